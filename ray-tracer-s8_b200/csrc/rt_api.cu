@@ -1,0 +1,648 @@
+// rt_api.cu — the C ABI of include/rt_b200.h: context, scene upload (+ host BVH build), render calls.
+//
+// Replaces the body of worker() in ray-tracer-slave/src/main.rs:32-106 (see the header for the mapping).
+// There is no CPU fallback anywhere in this file: every render goes through launch_render().
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <limits>
+#include <new>
+
+#include "rt_device.cuh"
+#include "rt_host.h"
+
+using namespace rtb;
+
+struct rt_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    int sm_count = 0, clock_khz = 0, smem_optin = 0;
+    char name[64] = {0};
+    uint8_t* d_out = nullptr;  // band / frame staging in HBM
+    size_t d_out_bytes = 0;
+    unsigned long long* d_ctr = nullptr;  // NUM_COUNTERS counters + tile ticket (last slot)
+    unsigned long long* h_ctr = nullptr;  // pinned mirror
+    float* d_scratch = nullptr;
+    std::string err;
+};
+
+struct rt_scene {
+    uint8_t* d_blob = nullptr;
+    size_t blob_bytes = 0;
+    DevScene dev{};
+    uint32_t n = 0, n_nodes = 0, depth = 0;
+    std::vector<uint32_t> rank_by_world;  // world position → DFS leaf rank
+};
+
+static thread_local std::string g_init_err = "";
+
+static int set_err(rt_ctx* ctx, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (ctx) ctx->err = buf;
+    else g_init_err = buf;
+    return code;
+}
+
+#define CK(ctx, call)                                                                                   \
+    do {                                                                                                \
+        cudaError_t e__ = (call);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return set_err(ctx, RT_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__),   \
+                           __FILE__, __LINE__);                                                         \
+    } while (0)
+
+extern "C" {
+
+int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
+
+const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
+
+int rt_init(int device, rt_ctx** out) {
+    if (!out) return set_err(nullptr, RT_ERR_INVALID_ARG, "rt_init: out is NULL");
+    *out = nullptr;
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0)
+        return set_err(nullptr, RT_ERR_NO_DEVICE, "no CUDA device (%s); this library has no CPU fallback",
+                       e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+    if (device < 0 || device >= count)
+        return set_err(nullptr, RT_ERR_INVALID_ARG, "device %d out of range [0,%d)", device, count);
+    rt_ctx* ctx = new (std::nothrow) rt_ctx();
+    if (!ctx) return set_err(nullptr, RT_ERR_INVALID_ARG, "out of host memory");
+    ctx->device = device;
+    cudaDeviceProp prop;
+#define CKI(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            set_err(nullptr, RT_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e__));            \
+            rt_shutdown(ctx);                                                                          \
+            return RT_ERR_CUDA;                                                                        \
+        }                                                                                              \
+    } while (0)
+    CKI(cudaSetDevice(device));
+    CKI(cudaGetDeviceProperties(&prop, device));
+    if (prop.major < 10) {
+        set_err(nullptr, RT_ERR_NO_DEVICE, "device %d is sm_%d%d; this build carries sm_100a code only", device,
+                prop.major, prop.minor);
+        rt_shutdown(ctx);
+        return RT_ERR_NO_DEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    ctx->smem_optin = (int)prop.sharedMemPerBlockOptin;
+    CKI(cudaDeviceGetAttribute(&ctx->clock_khz, cudaDevAttrClockRate, device));
+    memcpy(ctx->name, prop.name, 63); ctx->name[63] = 0;
+    CKI(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    CKI(cudaEventCreate(&ctx->ev0));
+    CKI(cudaEventCreate(&ctx->ev1));
+    CKI(cudaMalloc(&ctx->d_ctr, (NUM_COUNTERS + 1) * sizeof(unsigned long long)));
+    CKI(cudaMallocHost(&ctx->h_ctr, (NUM_COUNTERS + 1) * sizeof(unsigned long long)));
+#undef CKI
+    *out = ctx;
+    return RT_OK;
+}
+
+void rt_shutdown(rt_ctx* ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    if (ctx->d_out) cudaFree(ctx->d_out);
+    if (ctx->d_ctr) cudaFree(ctx->d_ctr);
+    if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
+    if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int rt_device_info(rt_ctx* ctx, int* sm_count, int* clock_khz, int* smem_optin, char name_out[64]) {
+    if (!ctx) return RT_ERR_INVALID_ARG;
+    if (sm_count) *sm_count = ctx->sm_count;
+    if (clock_khz) *clock_khz = ctx->clock_khz;
+    if (smem_optin) *smem_optin = ctx->smem_optin;
+    if (name_out) memcpy(name_out, ctx->name, 64);
+    return RT_OK;
+}
+
+void* rt_stream(rt_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+int rt_sync(rt_ctx* ctx) {
+    if (!ctx) return RT_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Scene
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+struct PrimRef {
+    uint8_t kind;  // 0 sphere, 1 triangle
+    uint32_t idx;  // index in the caller's array
+};
+
+// min_by / max_by with partial_cmp().unwrap_or(Equal) (mesh.rs:46-95): min_by returns the first
+// argument unless first > second; max_by returns the second unless first > second.
+inline float ref_min(float x, float y) { return (x > y) ? y : x; }
+inline float ref_max(float x, float y) { return (x > y) ? x : y; }
+
+inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+inline bool finite3(const float* v) { return std::isfinite(v[0]) && std::isfinite(v[1]) && std::isfinite(v[2]); }
+
+}  // namespace
+
+int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles,
+                    uint32_t n_triangles, const uint32_t* world_index, rt_scene** out) {
+    if (!ctx) return RT_ERR_INVALID_ARG;
+    if (!out) return set_err(ctx, RT_ERR_INVALID_ARG, "rt_scene_create: out is NULL");
+    *out = nullptr;
+    const uint64_t n64 = (uint64_t)n_spheres + n_triangles;
+    if (n64 == 0)
+        return set_err(ctx, RT_ERR_EMPTY_SCENE,
+                       "empty world: the reference's BVHNode::build never terminates on zero shapes");
+    if (n64 > 0x3fffffffu) return set_err(ctx, RT_ERR_UNSUPPORTED, "too many primitives");
+    if ((n_spheres && !spheres) || (n_triangles && !triangles))
+        return set_err(ctx, RT_ERR_INVALID_ARG, "rt_scene_create: NULL primitive array");
+    const uint32_t n = (uint32_t)n64;
+
+    // world order
+    std::vector<PrimRef> world(n);
+    {
+        std::vector<uint8_t> seen(n, 0);
+        for (uint32_t i = 0; i < n; i++) {
+            uint32_t pos = world_index ? world_index[i] : i;
+            if (pos >= n || seen[pos])
+                return set_err(ctx, RT_ERR_INVALID_ARG, "world_index is not a permutation of 0..%u", n - 1);
+            seen[pos] = 1;
+            world[pos] = i < n_spheres ? PrimRef{0, i} : PrimRef{1, i - n_spheres};
+        }
+    }
+    // bounds per world position (Sphere::aabb sphere.rs:65-72, Triangle::aabb mesh.rs:46-95)
+    std::vector<Box> boxes(n);
+    for (uint32_t w = 0; w < n; w++) {
+        Box& b = boxes[w];
+        if (world[w].kind == 0) {
+            const rt_sphere& s = spheres[world[w].idx];
+            if (!finite3(s.center) || !std::isfinite(s.radius))
+                return set_err(ctx, RT_ERR_BVH, "sphere %u has non-finite geometry", world[w].idx);
+            for (int a = 0; a < 3; a++) {
+                b.min[a] = s.center[a] - s.radius;
+                b.max[a] = s.center[a] + s.radius;
+            }
+        } else {
+            const rt_triangle& t = triangles[world[w].idx];
+            if (!finite3(t.a) || !finite3(t.b) || !finite3(t.c))
+                return set_err(ctx, RT_ERR_BVH, "triangle %u has non-finite geometry", world[w].idx);
+            for (int a = 0; a < 3; a++) {
+                b.min[a] = ref_min(ref_min(t.a[a], t.c[a]), t.b[a]);
+                b.max[a] = ref_max(ref_max(t.a[a], t.c[a]), t.b[a]);
+            }
+        }
+    }
+    HostBVH bvh;
+    std::string berr;
+    if (!build_bvh(boxes, &bvh, &berr)) return set_err(ctx, RT_ERR_BVH, "BVH build failed: %s", berr.c_str());
+    if (bvh.depth > (uint32_t)MAX_STACK)
+        return set_err(ctx, RT_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack (%d)", bvh.depth, MAX_STACK);
+
+    // pids: spheres then triangles, each in DFS leaf order
+    std::vector<uint32_t> pid_of_world(n), rank_of_world(n);
+    uint32_t next_s = 0, next_t = n_spheres;
+    for (uint32_t r = 0; r < n; r++) {
+        uint32_t w = bvh.leaf_order[r];
+        rank_of_world[w] = r;
+        pid_of_world[w] = world[w].kind == 0 ? next_s++ : next_t++;
+    }
+    const uint32_t ni = (uint32_t)bvh.inner.size();
+
+    // blob layout (each section 256-byte aligned)
+    size_t off = 0;
+    auto take = [&](size_t bytes) {
+        size_t o = off;
+        off = align_up(off + bytes, 256);
+        return o;
+    };
+    const size_t o_sph = take((size_t)n_spheres * 16), o_tri = take((size_t)n_triangles * 64);
+    const size_t o_na = take((size_t)ni * 16), o_nb = take((size_t)ni * 16), o_nc = take((size_t)ni * 16);
+    const size_t o_nd = take((size_t)ni * 8), o_mat = take((size_t)n * 16), o_em = take((size_t)n * 4);
+    const size_t o_rank = take((size_t)n * 4);
+    std::vector<uint8_t> blob(off ? off : 256, 0);
+    float* h_sph = (float*)(blob.data() + o_sph);
+    float* h_tri = (float*)(blob.data() + o_tri);
+    float* h_na = (float*)(blob.data() + o_na);
+    float* h_nb = (float*)(blob.data() + o_nb);
+    float* h_nc = (float*)(blob.data() + o_nc);
+    int32_t* h_nd = (int32_t*)(blob.data() + o_nd);
+    float* h_mat = (float*)(blob.data() + o_mat);
+    float* h_em = (float*)(blob.data() + o_em);
+    uint32_t* h_rank = (uint32_t*)(blob.data() + o_rank);
+
+    for (uint32_t w = 0; w < n; w++) {
+        const uint32_t pid = pid_of_world[w];
+        h_rank[pid] = rank_of_world[w];
+        if (world[w].kind == 0) {
+            const rt_sphere& s = spheres[world[w].idx];
+            float* g = h_sph + 4 * (size_t)pid;
+            g[0] = s.center[0]; g[1] = s.center[1]; g[2] = s.center[2];
+            g[3] = s.radius * s.radius;  // radius.powi(2)
+            float* m = h_mat + 4 * (size_t)pid;
+            m[0] = s.albedo[0]; m[1] = s.albedo[1]; m[2] = s.albedo[2]; m[3] = s.roughness;
+            h_em[pid] = s.emission;
+        } else {
+            const rt_triangle& t = triangles[world[w].idx];
+            float* g = h_tri + 16 * (size_t)(pid - n_spheres);
+            float ab[3], ac[3], amb[3], amc[3];
+            for (int a = 0; a < 3; a++) {
+                ab[a] = t.b[a] - t.a[a];   // a_to_b (mesh.rs:111)
+                ac[a] = t.c[a] - t.a[a];   // a_to_c
+                amb[a] = t.a[a] - t.b[a];  // normal_at: (a-b).cross(a-c) (mesh.rs:164)
+                amc[a] = t.a[a] - t.c[a];
+            }
+            // glam cross + normalize_or_zero, single f32 ops (host built with -ffp-contract=off)
+            float cr[3] = {amb[1] * amc[2] - amc[1] * amb[2], amb[2] * amc[0] - amc[2] * amb[0],
+                           amb[0] * amc[1] - amc[0] * amb[1]};
+            float dd = (cr[0] * cr[0] + cr[1] * cr[1]) + cr[2] * cr[2];
+            float rcp = 1.0f / sqrtf(dd);
+            float nrm[3] = {0.0f, 0.0f, 0.0f};
+            if (std::isfinite(rcp) && rcp > 0.0f) {
+                nrm[0] = cr[0] * rcp; nrm[1] = cr[1] * rcp; nrm[2] = cr[2] * rcp;
+            }
+            for (int a = 0; a < 3; a++) {
+                g[0 + a] = t.a[a];
+                g[4 + a] = ab[a];
+                g[8 + a] = ac[a];
+                g[12 + a] = nrm[a];
+            }
+            float* m = h_mat + 4 * (size_t)pid;
+            m[0] = t.albedo[0]; m[1] = t.albedo[1]; m[2] = t.albedo[2]; m[3] = t.roughness;
+            h_em[pid] = t.emission;
+        }
+    }
+    auto code_of = [&](int32_t c) -> int32_t { return c >= 0 ? c : ~(int32_t)pid_of_world[(uint32_t)~c]; };
+    auto padded = [](const Box& b, float lo[3], float hi[3]) {
+        // conservative culling: pad by a few ulp of the largest coordinate (FILTER-domain slab tests)
+        float m = 0.0f;
+        for (int a = 0; a < 3; a++) m = fmaxf(m, fmaxf(fabsf(b.min[a]), fabsf(b.max[a])));
+        const float pad = m * 4e-6f + 1e-30f;
+        for (int a = 0; a < 3; a++) {
+            lo[a] = b.min[a] - pad;
+            hi[a] = b.max[a] + pad;
+        }
+    };
+    for (uint32_t i = 0; i < ni; i++) {
+        const HostNode& hn = bvh.inner[i];
+        float ll[3], lh[3], rl[3], rh[3];
+        padded(hn.box_l, ll, lh);
+        padded(hn.box_r, rl, rh);
+        float* a = h_na + 4 * (size_t)i;
+        float* b = h_nb + 4 * (size_t)i;
+        float* c = h_nc + 4 * (size_t)i;
+        a[0] = ll[0]; a[1] = ll[1]; a[2] = ll[2]; a[3] = lh[0];
+        b[0] = lh[1]; b[1] = lh[2]; b[2] = rl[0]; b[3] = rl[1];
+        c[0] = rl[2]; c[1] = rh[0]; c[2] = rh[1]; c[3] = rh[2];
+        h_nd[2 * (size_t)i] = code_of(hn.left);
+        h_nd[2 * (size_t)i + 1] = code_of(hn.right);
+    }
+
+    rt_scene* sc = new (std::nothrow) rt_scene();
+    if (!sc) return set_err(ctx, RT_ERR_INVALID_ARG, "out of host memory");
+    sc->n = n;
+    sc->n_nodes = bvh.node_count;
+    sc->depth = bvh.depth;
+    sc->rank_by_world = rank_of_world;
+    sc->blob_bytes = blob.size();
+    cudaError_t e = cudaSetDevice(ctx->device);
+    if (e == cudaSuccess) e = cudaMalloc(&sc->d_blob, blob.size());
+    if (e == cudaSuccess) e = cudaMemcpyAsync(sc->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+        if (sc->d_blob) cudaFree(sc->d_blob);
+        delete sc;
+        return set_err(ctx, RT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
+    }
+    DevScene& d = sc->dev;
+    d.sph = (const float4*)(sc->d_blob + o_sph);
+    d.tri = (const float4*)(sc->d_blob + o_tri);
+    d.node_a = (const float4*)(sc->d_blob + o_na);
+    d.node_b = (const float4*)(sc->d_blob + o_nb);
+    d.node_c = (const float4*)(sc->d_blob + o_nc);
+    d.node_d = (const int2*)(sc->d_blob + o_nd);
+    d.mat = (const float4*)(sc->d_blob + o_mat);
+    d.emis = (const float*)(sc->d_blob + o_em);
+    d.rank = (const uint32_t*)(sc->d_blob + o_rank);
+    d.ns = n_spheres;
+    d.nt = n_triangles;
+    d.ni = ni;
+    d.root = code_of(bvh.root);
+    *out = sc;
+    return RT_OK;
+}
+
+void rt_scene_destroy(rt_ctx* ctx, rt_scene* scene) {
+    if (!scene) return;
+    if (ctx) {
+        cudaSetDevice(ctx->device);
+        cudaStreamSynchronize(ctx->stream);
+    }
+    if (scene->d_blob) cudaFree(scene->d_blob);
+    delete scene;
+}
+
+int rt_scene_info(const rt_scene* scene, uint32_t* n_prims, uint32_t* n_nodes, uint32_t* depth, uint32_t* rank_out) {
+    if (!scene) return RT_ERR_INVALID_ARG;
+    if (n_prims) *n_prims = scene->n;
+    if (n_nodes) *n_nodes = scene->n_nodes;
+    if (depth) *depth = scene->depth;
+    if (rank_out) memcpy(rank_out, scene->rank_by_world.data(), scene->n * sizeof(uint32_t));
+    return RT_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Render
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+struct Resolved {
+    rt_params p;
+    DevCamera cam;
+    int isect;
+};
+
+// Brute force wins below this many primitives (measured crossover)
+constexpr uint32_t kBruteMaxPrims = 96;
+
+int resolve(rt_ctx* ctx, const rt_scene* scene, const rt_params* in, Resolved* r) {
+    if (!scene || !in) return set_err(ctx, RT_ERR_INVALID_ARG, "NULL scene or params");
+    rt_params p = *in;
+    if (p.divisions == 0) p.divisions = 1;
+    if (p.spp == 0) p.spp = 100;                 // main.rs:51
+    if (p.max_bounces == 0) p.max_bounces = 10;  // main.rs:39
+    if (p.aperture == 0.0f) p.aperture = 0.1f;   // main.rs:45
+    if (p.focus_distance == 0.0f) p.focus_distance = 1.0f;
+    if (p.field_of_view == 0.0f) p.field_of_view = 3.14159265358979323846f / 2.0f;  // PI / 2f32
+    if (p.focal_length == 0.0f) p.focal_length = 1.0f;
+    if (p.width == 0 || p.height == 0) return set_err(ctx, RT_ERR_INVALID_ARG, "zero width or height");
+    if (p.height % p.divisions != 0)
+        return set_err(ctx, RT_ERR_INVALID_ARG,
+                       "height %u is not a multiple of divisions %u (the reference silently drops rows)", p.height,
+                       p.divisions);
+    if (p.division_no >= p.divisions) return set_err(ctx, RT_ERR_INVALID_ARG, "division_no out of range");
+    if (p.max_bounces + 1 > (uint32_t)MAX_PATH)
+        return set_err(ctx, RT_ERR_UNSUPPORTED, "max_bounces %u exceeds this build's limit %d", p.max_bounces, MAX_PATH - 1);
+    if ((uint64_t)p.width * p.height > 0x7fffffffu) return set_err(ctx, RT_ERR_UNSUPPORTED, "frame too large");
+    if (p.intersector > RT_INTERSECT_BVH) return set_err(ctx, RT_ERR_INVALID_ARG, "unknown intersector");
+    r->p = p;
+    r->isect = p.intersector == RT_INTERSECT_AUTO ? (scene->n <= kBruteMaxPrims ? RT_INTERSECT_BRUTE : RT_INTERSECT_BVH)
+                                                  : (int)p.intersector;
+    // Camera::new (camera.rs:19-47) with the arguments of main.rs:42-50, single f32 ops in order
+    DevCamera& c = r->cam;
+    const float aspect = (float)p.width / (float)p.height;
+    const float image_height = (float)p.height;
+    const float vh = 2.0f * tanf(p.field_of_view / 2.0f);
+    const float vw = aspect * vh;
+    const float hor[3] = {vw, 0.0f, 0.0f}, ver[3] = {0.0f, vh, 0.0f}, fl[3] = {0.0f, 0.0f, p.focal_length};
+    for (int a = 0; a < 3; a++) {
+        c.org[a] = p.cam_origin[a];
+        c.hor[a] = hor[a];
+        c.ver[a] = ver[a];
+        c.llc[a] = ((p.cam_origin[a] - hor[a] / 2.0f) - ver[a] / 2.0f) - fl[a];
+    }
+    c.lens_radius = p.aperture / 2.0f;
+    c.u_den = aspect * image_height - 1.0f;
+    c.v_den = image_height - 1.0f;
+    c.focus = p.focus_distance;
+    return RT_OK;
+}
+
+int ensure_out(rt_ctx* ctx, size_t bytes) {
+    if (ctx->d_out_bytes >= bytes) return RT_OK;
+    if (ctx->d_out) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaFree(ctx->d_out));
+        ctx->d_out = nullptr;
+        ctx->d_out_bytes = 0;
+    }
+    CK(ctx, cudaMalloc(&ctx->d_out, bytes));
+    ctx->d_out_bytes = bytes;
+    return RT_OK;
+}
+
+// Launches the render of global rows [row0,row1) (tiles of this rank only) into `dst` whose row 0 is
+// global row out_row0.  Leaves timing events recorded on the stream.
+int launch(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, uint32_t row0, uint32_t row1, uint32_t tile_rank,
+           uint32_t tile_ranks, uint8_t* dst, uint32_t out_row0, LaunchInfo* info) {
+    DevParams pr{};
+    pr.width = r.p.width;
+    pr.height = r.p.height;
+    pr.row0 = row0;
+    pr.row1 = row1;
+    pr.spp = r.p.spp;
+    pr.depth = r.p.max_bounces + 1;
+    pr.seed = r.p.seed;
+    pr.tile_rank = tile_rank;
+    pr.tile_ranks = tile_ranks;
+    pr.out = dst;
+    pr.out_row0 = out_row0;
+    pr.tiles_x = (r.p.width + TILE_W - 1) / TILE_W;
+    pr.tiles_y = (row1 - row0 + TILE_H - 1) / TILE_H;
+    pr.counters = ctx->d_ctr;
+    pr.tile_counter = reinterpret_cast<unsigned int*>(ctx->d_ctr + NUM_COUNTERS);
+    CK(ctx, cudaMemsetAsync(ctx->d_ctr, 0, (NUM_COUNTERS + 1) * sizeof(unsigned long long), ctx->stream));
+    CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(ctx, launch_render(scene->dev, r.cam, pr, r.isect, r.p.collect_counters != 0, ctx->sm_count, ctx->smem_optin,
+                          ctx->stream, info));
+    CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+    return RT_OK;
+}
+
+int finish_stats(rt_ctx* ctx, const Resolved& r, uint64_t pixels, rt_stats* st,
+                 std::chrono::steady_clock::time_point t0) {
+    if (!st) return RT_OK;
+    CK(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, NUM_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
+                            ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    memset(st, 0, sizeof *st);
+    const unsigned long long* c = ctx->h_ctr;
+    st->rays = c[CTR_RAYS];
+    st->primary = pixels * r.p.spp;
+    st->slab_tests = c[CTR_SLAB];
+    st->sphere_tests = c[CTR_SPH_TEST];
+    st->sphere_exact = c[CTR_SPH_EXACT];
+    st->tri_tests = c[CTR_TRI_TEST];
+    st->hits = c[CTR_HITS];
+    st->shades = c[CTR_SHADES];
+    st->emissive = c[CTR_EMISSIVE];
+    st->sky = c[CTR_SKY];
+    st->active_lane_iters = c[CTR_ACTIVE_LANES];
+    st->total_lane_iters = c[CTR_TOTAL_LANES];
+    float ms = 0.0f;
+    CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+    st->kernel_ms = ms;
+    st->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    st->intersector_used = (uint32_t)r.isect;
+    st->kernel_launches = 1;
+    return RT_OK;
+}
+
+int render_rows_to_host(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, uint32_t row0, uint32_t row1,
+                        uint8_t* out_rgb, size_t out_len, rt_stats* stats) {
+    auto t0 = std::chrono::steady_clock::now();
+    const size_t bytes = (size_t)(row1 - row0) * r.p.width * 3;
+    if (!out_rgb) return set_err(ctx, RT_ERR_INVALID_ARG, "out_rgb is NULL");
+    if (out_len != bytes)
+        return set_err(ctx, RT_ERR_INVALID_ARG, "out_len %zu != (rows %u * width %u * 3) = %zu", out_len, row1 - row0,
+                       r.p.width, bytes);
+    CK(ctx, cudaSetDevice(ctx->device));
+    int rc = ensure_out(ctx, bytes);
+    if (rc) return rc;
+    rc = launch(ctx, scene, r, row0, row1, 0, 1, ctx->d_out, row0, nullptr);
+    if (rc) return rc;
+    CK(ctx, cudaMemcpyAsync(out_rgb, ctx->d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return finish_stats(ctx, r, (uint64_t)(row1 - row0) * r.p.width, stats, t0);
+}
+
+}  // namespace
+
+int rt_render_division(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint8_t* out_rgb, size_t out_len,
+                       rt_stats* stats) {
+    if (!ctx) return RT_ERR_INVALID_ARG;
+    Resolved r;
+    int rc = resolve(ctx, scene, params, &r);
+    if (rc) return rc;
+    const uint32_t band = r.p.height / r.p.divisions;  // main.rs:55-56
+    const uint32_t row0 = band * r.p.division_no;      // main.rs:66-68
+    return render_rows_to_host(ctx, scene, r, row0, row0 + band, out_rgb, out_len, stats);
+}
+
+int rt_render_frame(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint8_t* out_rgb, size_t out_len,
+                    rt_stats* stats) {
+    if (!ctx) return RT_ERR_INVALID_ARG;
+    Resolved r;
+    rt_params p;
+    if (params) {
+        p = *params;
+        p.division_no = 0;
+    }
+    int rc = resolve(ctx, scene, params ? &p : nullptr, &r);
+    if (rc) return rc;
+    return render_rows_to_host(ctx, scene, r, 0, r.p.height, out_rgb, out_len, stats);
+}
+
+int rt_render_tiles_device(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint32_t tile_rank,
+                           uint32_t tile_ranks, void* frame_dev, int sync, rt_stats* stats) {
+    if (!ctx) return RT_ERR_INVALID_ARG;
+    auto t0 = std::chrono::steady_clock::now();
+    Resolved r;
+    rt_params p;
+    if (params) {
+        p = *params;
+        p.division_no = 0;
+    }
+    int rc = resolve(ctx, scene, params ? &p : nullptr, &r);
+    if (rc) return rc;
+    if (!frame_dev) return set_err(ctx, RT_ERR_INVALID_ARG, "frame_dev is NULL");
+    if (tile_ranks == 0 || tile_rank >= tile_ranks) return set_err(ctx, RT_ERR_INVALID_ARG, "bad tile_rank/tile_ranks");
+    CK(ctx, cudaSetDevice(ctx->device));
+    rc = launch(ctx, scene, r, 0, r.p.height, tile_rank, tile_ranks, (uint8_t*)frame_dev, 0, nullptr);
+    if (rc) return rc;
+    if (sync) {
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        // pixel count of this rank's tiles is not needed by callers; report the frame total / ranks
+        return finish_stats(ctx, r, (uint64_t)r.p.width * r.p.height / tile_ranks, stats, t0);
+    }
+    return RT_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Memory helpers
+// -------------------------------------------------------------------------------------------------
+int rt_host_alloc(rt_ctx* ctx, size_t bytes, void** out) {
+    if (!ctx || !out) return RT_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMallocHost(out, bytes ? bytes : 1));
+    return RT_OK;
+}
+void rt_host_free(rt_ctx* ctx, void* p) {
+    if (ctx) cudaSetDevice(ctx->device);
+    if (p) cudaFreeHost(p);
+}
+
+int rt_frame_alloc(rt_ctx* ctx, size_t bytes, void** dev_out, uint8_t handle_out[64]) {
+    if (!ctx || !dev_out) return RT_ERR_INVALID_ARG;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "IPC handle size");
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMalloc(dev_out, bytes ? bytes : 1));
+    if (handle_out) {
+        cudaIpcMemHandle_t h;
+        CK(ctx, cudaIpcGetMemHandle(&h, *dev_out));
+        memcpy(handle_out, &h, 64);
+    }
+    return RT_OK;
+}
+int rt_frame_open(rt_ctx* ctx, const uint8_t handle[64], void** dev_out) {
+    if (!ctx || !handle || !dev_out) return RT_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    memcpy(&h, handle, 64);
+    CK(ctx, cudaIpcOpenMemHandle(dev_out, h, cudaIpcMemLazyEnablePeerAccess));
+    return RT_OK;
+}
+int rt_frame_close(rt_ctx* ctx, void* dev) {
+    if (!ctx) return RT_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaIpcCloseMemHandle(dev));
+    return RT_OK;
+}
+int rt_frame_free(rt_ctx* ctx, void* dev) {
+    if (!ctx) return RT_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    CK(ctx, cudaFree(dev));
+    return RT_OK;
+}
+int rt_frame_download(rt_ctx* ctx, const void* frame_dev, uint8_t* out_rgb, size_t bytes) {
+    if (!ctx || !frame_dev || !out_rgb) return RT_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    CK(ctx, cudaMemcpyAsync(out_rgb, frame_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(ctx, cudaStreamSynchronize(ctx->stream));
+    return RT_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// FP32 roofline denominator
+// -------------------------------------------------------------------------------------------------
+int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops_out, float* ms_out) {
+    if (!ctx || !tflops_out) return RT_ERR_INVALID_ARG;
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (!ctx->d_scratch) CK(ctx, cudaMalloc(&ctx->d_scratch, (size_t)ctx->sm_count * 8 * 256 * sizeof(float)));
+    const int iters = 4096;
+    float best = std::numeric_limits<float>::max();
+    for (int rep = 0; rep < 4; rep++) {
+        CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+        CK(ctx, launch_fp32_peak(ctx->d_scratch, ctx->sm_count, iters, ctx->stream));
+        CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        float ms = 0.0f;
+        CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+        if (rep > 0 && ms < best) best = ms;
+    }
+    const double flops = (double)ctx->sm_count * 8 * 256 * (double)iters * 16 * 8 * 2;
+    *tflops_out = flops / (best * 1e-3) / 1e12;
+    if (ms_out) *ms_out = best;
+    return RT_OK;
+}
+
+}  // extern "C"

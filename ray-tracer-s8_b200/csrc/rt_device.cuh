@@ -1,0 +1,260 @@
+// rt_device.cuh — device-side building blocks of the render path (sm_100a).
+//
+// Two arithmetic domains live side by side:
+//   * EXACT  (x_* helpers): single IEEE-754 round-to-nearest f32 operations in the reference's
+//     operation order (glam 0.23 Vec3A/SSE2, roots 0.0.8, rand 0.8.5,
+//     rand_distr 0.4.3).  Built only from __fadd_rn/__fmul_rn/__fdiv_rn/__fsqrt_rn, which nvcc never
+//     contracts into FFMA, so the results are bit-identical to the CPU's SSE scalar ops.  Everything
+//     that decides a path (roots, t-range, nearest hit, scatter direction, colour) is EXACT.
+//   * FILTER (plain fmaf / fminf / fmaxf): conservative culling only (sphere discriminant pre-test,
+//     BVH slab tests).  A filter may let a miss through; it must never reject an exact hit.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace rtb {
+
+constexpr int TILE_W = 8;        // a warp renders an 8x4-pixel tile
+constexpr int TILE_H = 4;
+constexpr int MAX_STACK = 64;    // BVH traversal stack entries (host rejects deeper trees)
+constexpr int MAX_PATH = 64;     // max_bounces + 1 <= MAX_PATH
+constexpr float T_MIN = 0.001f;  // shapes/mod.rs:12
+constexpr float T_MAX = 1000.0f; // shapes/mod.rs:13
+
+// ---------------------------------------------------------------------------------------------
+// Scene in HBM (structure of arrays).  Primitive id ("pid"): [0,ns) spheres, [ns,ns+nt) triangles,
+// both stored in the DFS leaf order of the reference BVH.  BVH child code: >= 0 inner node index,
+// < 0 leaf with pid = ~code.
+// ---------------------------------------------------------------------------------------------
+struct DevScene {
+    const float4* sph;     // [ns]    cx, cy, cz, r*r
+    const float4* tri;     // [nt*4]  a | b-a | c-a | normalize_or_zero((a-b)x(a-c))
+    const float4* node_a;  // [ni]    l.min.xyz, l.max.x
+    const float4* node_b;  // [ni]    l.max.yz,  r.min.xy
+    const float4* node_c;  // [ni]    r.min.z,   r.max.xyz
+    const int2* node_d;    // [ni]    left code, right code
+    const float4* mat;     // [ns+nt] albedo rgb, roughness
+    const float* emis;     // [ns+nt]
+    const uint32_t* rank;  // [ns+nt] DFS leaf rank (exact-distance tie-break, shapes/mod.rs:177-182)
+    uint32_t ns, nt, ni;
+    int root;              // child code of the root
+};
+
+struct DevCamera {            // Camera::new (camera.rs:19-47), evaluated on the host in reference order
+    float org[3], llc[3], hor[3], ver[3];
+    float lens_radius;        // aperture / 2
+    float u_den, v_den;       // aspect*image_height - 1, image_height - 1
+    float focus;
+};
+
+struct DevParams {
+    uint32_t width, height;
+    uint32_t row0, row1;         // global image rows [row0,row1) rendered by this launch
+    uint32_t spp, depth;         // depth = max_bounces + 1 nearest-hit queries per sample at most
+    uint64_t seed;
+    uint32_t tile_rank, tile_ranks;
+    uint8_t* out;                // RGB8; buffer row 0 = global row out_row0
+    uint32_t out_row0;
+    uint32_t tiles_x, tiles_y;
+    unsigned int* tile_counter;  // zeroed before launch
+    unsigned long long* counters;  // NUM_COUNTERS
+};
+
+enum CounterSlot {
+    CTR_RAYS = 0, CTR_SLAB, CTR_SPH_TEST, CTR_SPH_EXACT, CTR_TRI_TEST, CTR_HITS, CTR_SHADES, CTR_EMISSIVE,
+    CTR_SKY, CTR_ACTIVE_LANES, CTR_TOTAL_LANES, NUM_COUNTERS
+};
+
+// ---------------------------------------------------------------------------------------------
+// EXACT domain
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float x_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float x_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float x_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float x_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float x_sqrt(float a) { return __fsqrt_rn(a); }
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+__device__ __forceinline__ V3 x_add(V3 a, V3 b) { return mk(x_add(a.x, b.x), x_add(a.y, b.y), x_add(a.z, b.z)); }
+__device__ __forceinline__ V3 x_sub(V3 a, V3 b) { return mk(x_sub(a.x, b.x), x_sub(a.y, b.y), x_sub(a.z, b.z)); }
+__device__ __forceinline__ V3 x_scale(V3 a, float s) { return mk(x_mul(a.x, s), x_mul(a.y, s), x_mul(a.z, s)); }
+// glam dot3: (x*x' + y*y') + z*z'
+__device__ __forceinline__ float x_dot(V3 a, V3 b) {
+    return x_add(x_add(x_mul(a.x, b.x), x_mul(a.y, b.y)), x_mul(a.z, b.z));
+}
+__device__ __forceinline__ float x_length(V3 a) { return x_sqrt(x_dot(a, a)); }
+// glam cross: (a.zxy*b - a*b.zxy).zxy
+__device__ __forceinline__ V3 x_cross(V3 a, V3 b) {
+    return mk(x_sub(x_mul(a.y, b.z), x_mul(b.y, a.z)), x_sub(x_mul(a.z, b.x), x_mul(b.z, a.x)),
+              x_sub(x_mul(a.x, b.y), x_mul(b.x, a.y)));
+}
+// Vec3A::normalize: v / sqrt(dot) per lane (used by Ray::new, ray.rs:134)
+__device__ __forceinline__ V3 x_normalize_div(V3 a) {
+    float l = x_length(a);
+    return mk(x_div(a.x, l), x_div(a.y, l), x_div(a.z, l));
+}
+// Vec3A::try_normalize: rcp = 1/length; Some(v*rcp) iff rcp finite && rcp > 0
+__device__ __forceinline__ bool x_try_normalize(V3 a, V3* out) {
+    float rcp = x_div(1.0f, x_length(a));
+    if (isfinite(rcp) && rcp > 0.0f) {
+        *out = x_scale(a, rcp);
+        return true;
+    }
+    return false;
+}
+__device__ __forceinline__ V3 x_normalize_or_zero(V3 a) {
+    V3 r;
+    if (x_try_normalize(a, &r)) return r;
+    return mk(0.0f, 0.0f, 0.0f);
+}
+
+// rand 0.8.5 SmallRng on 64-bit targets = xoshiro256++; seed_from_u64 = 4 SplitMix64 outputs
+struct Rng {
+    uint64_t s0, s1, s2, s3;
+    __device__ __forceinline__ static uint64_t rotl(uint64_t x, int k) { return (x << k) | (x >> (64 - k)); }
+    __device__ __forceinline__ static uint64_t splitmix(uint64_t& st) {
+        st += 0x9e3779b97f4a7c15ull;
+        uint64_t z = st;
+        z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+        z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+        return z ^ (z >> 31);
+    }
+    __device__ __forceinline__ void seed_from_u64(uint64_t st) {
+        s0 = splitmix(st);
+        s1 = splitmix(st);
+        s2 = splitmix(st);
+        s3 = splitmix(st);
+        if ((s0 | s1 | s2 | s3) == 0) {  // from_seed: all-zero → seed_from_u64(0)
+            uint64_t z = 0;
+            s0 = splitmix(z);
+            s1 = splitmix(z);
+            s2 = splitmix(z);
+            s3 = splitmix(z);
+        }
+    }
+    __device__ __forceinline__ uint32_t next_u32() {  // high half of next_u64
+        uint64_t result = rotl(s0 + s3, 23) + s0;
+        uint64_t t = s1 << 17;
+        s2 ^= s0;
+        s3 ^= s1;
+        s1 ^= s2;
+        s0 ^= s3;
+        s2 ^= t;
+        s3 = rotl(s3, 45);
+        return (uint32_t)(result >> 32);
+    }
+    // UniformFloat<f32>: 23 mantissa bits into [1,2), minus 1
+    __device__ __forceinline__ float value0_1() {
+        return x_sub(__uint_as_float(0x3f800000u | (next_u32() >> 9)), 1.0f);
+    }
+    // gen_range(0f32..1f32): value0_1 * 1 + 0
+    __device__ __forceinline__ float gen_range_0_1() { return x_add(x_mul(value0_1(), 1.0f), 0.0f); }
+    // Uniform::new(-1,1).sample: value0_1 * 2 + (-1)
+    __device__ __forceinline__ float uniform_m1_1() { return x_add(x_mul(value0_1(), 2.0f), -1.0f); }
+};
+
+// rand_distr 0.4.3 UnitDisc: rejection, accept x1^2 + x2^2 <= 1
+__device__ __forceinline__ void unit_disc(Rng& rng, float& a, float& b) {
+    for (;;) {
+        a = rng.uniform_m1_1();
+        b = rng.uniform_m1_1();
+        if (x_add(x_mul(a, a), x_mul(b, b)) <= 1.0f) break;
+    }
+}
+// rand_distr 0.4.3 UnitSphere (Marsaglia 1972)
+__device__ __forceinline__ V3 unit_sphere(Rng& rng) {
+    for (;;) {
+        float x1 = rng.uniform_m1_1();
+        float x2 = rng.uniform_m1_1();
+        float sum = x_add(x_mul(x1, x1), x_mul(x2, x2));
+        if (sum >= 1.0f) continue;
+        float factor = x_mul(2.0f, x_sqrt(x_sub(1.0f, sum)));
+        return mk(x_mul(x1, factor), x_mul(x2, factor), x_sub(1.0f, x_mul(2.0f, sum)));
+    }
+}
+
+__device__ __forceinline__ bool in_range(float t) { return t >= T_MIN && t < T_MAX; }
+
+// Sphere::get_roots (sphere.rs:42-47) + find_roots_quadratic (roots 0.0.8) + root pick
+// (shapes/mod.rs:106-129).  oc = origin - center (exact), r2 = radius*radius (exact).
+// Returns true and the chosen in-range root.
+__device__ __forceinline__ bool sphere_root_exact(V3 d, V3 oc, float r2, float* t_out) {
+    float b = x_dot(x_scale(d, 2.0f), oc);  // (2*d).dot(o - c)
+    float l = x_length(oc);
+    float c = x_sub(x_mul(l, l), r2);       // length().powi(2) - radius.powi(2)
+    float disc = x_sub(x_mul(b, b), x_mul(4.0f, c));  // a1*a1 - 4*a2*a0, a2 = 1
+    if (disc < 0.0f) return false;
+    if (disc == 0.0f) {
+        float x = x_div(-b, 2.0f);
+        if (!in_range(x)) return false;
+        *t_out = x;
+        return true;
+    }
+    float sq = x_sqrt(disc);
+    float same_sign, diff_sign;
+    if (b < 0.0f) {
+        same_sign = x_add(-b, sq);
+        diff_sign = x_sub(-b, sq);
+    } else {
+        same_sign = x_sub(-b, sq);
+        diff_sign = x_add(-b, sq);
+    }
+    float x1, x2;
+    if (fabsf(same_sign) > 2.0f) {
+        float a0x2 = x_mul(2.0f, c);
+        x1 = x_div(a0x2, same_sign);
+        x2 = (fabsf(diff_sign) > 2.0f) ? x_div(a0x2, diff_sign) : x_div(same_sign, 2.0f);
+    } else {
+        x1 = x_div(diff_sign, 2.0f);
+        x2 = x_div(same_sign, 2.0f);
+    }
+    float lo, hi;
+    if (x1 < x2) {
+        lo = x1;
+        hi = x2;
+    } else {
+        lo = x2;
+        hi = x1;
+    }
+    bool li = in_range(lo), hi_in = in_range(hi);
+    if (li && hi_in) {
+        *t_out = lo < hi ? lo : hi;
+        return true;
+    }
+    if (li) {
+        *t_out = lo;
+        return true;
+    }
+    if (hi_in) {
+        *t_out = hi;
+        return true;
+    }
+    return false;
+}
+
+// Triangle::get_roots (mesh.rs:109-161), two-sided Moeller-Trumbore, + t-range (shapes/mod.rs:109-115)
+__device__ __forceinline__ bool triangle_root_exact(V3 o, V3 d, V3 a, V3 ab, V3 ac, float* t_out) {
+    const float EPSILON = 0.00001f;
+    V3 u_vec = x_cross(d, ac);
+    float det = x_dot(ab, u_vec);
+    if (det < EPSILON && det > -EPSILON) return false;
+    float inv_det = x_div(1.0f, det);
+    V3 ao = x_sub(o, a);
+    float u = x_mul(x_dot(ao, u_vec), inv_det);
+    if (!(u >= 0.0f && u <= 1.0f)) return false;
+    V3 v_vec = x_cross(ao, ab);
+    float v = x_mul(x_dot(d, v_vec), inv_det);
+    if (v < 0.0f || x_add(u, v) > 1.0f) return false;
+    float dist = x_mul(x_dot(ac, v_vec), inv_det);
+    if (!(dist > EPSILON)) return false;
+    if (!in_range(dist)) return false;
+    *t_out = dist;
+    return true;
+}
+
+__device__ __forceinline__ V3 ld3(const float4& v) { return mk(v.x, v.y, v.z); }
+
+}  // namespace rtb

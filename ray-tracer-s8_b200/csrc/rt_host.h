@@ -1,0 +1,49 @@
+// rt_host.h — host-side declarations shared by rt_api.cu, rt_kernels.cu and rt_bvh_host.cpp.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/rt_b200.h"
+
+namespace rtb {
+
+struct DevScene;
+struct DevCamera;
+struct DevParams;
+
+struct LaunchInfo {
+    unsigned grid = 0, threads = 0;
+    size_t dyn_smem = 0;
+    int ctas_per_sm = 0;
+    bool scene_in_smem = false;
+};
+
+// rt_kernels.cu
+cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevParams& pr, int isect, bool count,
+                          int sm_count, int smem_optin, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_fp32_peak(float* scratch, int sm_count, int iters, cudaStream_t stream);
+size_t scene_smem_bytes(const DevScene& sc, int isect);
+
+// ---- rt_bvh_host.cpp: SAH BVH with the reference's topology ------------------------------------------
+struct Box {
+    float min[3], max[3];
+};
+struct HostNode {       // inner node; children are codes: >= 0 inner index, < 0 leaf of world position ~code
+    Box box_l, box_r;
+    int32_t left, right;
+};
+struct HostBVH {
+    std::vector<HostNode> inner;        // DFS pre-order
+    std::vector<uint32_t> leaf_order;   // rank → world position
+    int32_t root = 0;                   // code
+    uint32_t depth = 0;                 // deepest leaf (root = 0)
+    uint32_t node_count = 0;            // inner + leaves, = 2n-1
+};
+// boxes[i] = AABB of the primitive at world position i.  Returns false (with a message) when the
+// reference's build would panic or never terminate.
+bool build_bvh(const std::vector<Box>& boxes, HostBVH* out, std::string* err);
+
+}  // namespace rtb
