@@ -92,24 +92,33 @@ typedef struct rt_params {
 typedef struct rt_stats {
     uint64_t rays;          /* nearest-hit queries = ray_color calls with depth > 0 (always filled) */
     uint64_t primary;       /* camera rays = pixels * spp (always filled) */
-    uint64_t slab_tests;    /* child-box tests during BVH traversal          (collect_counters) */
-    uint64_t sphere_tests;  /* sphere candidate tests                        (collect_counters) */
+    /* the rest is filled only when params.collect_counters != 0 (instrumented kernel variant) */
+    uint64_t slab_tests;    /* child-box tests during BVH traversal */
+    uint64_t sphere_tests;  /* sphere candidate tests (discriminant filter) */
     uint64_t sphere_exact;  /* ... that went through the exact reference arithmetic */
-    uint64_t tri_tests;     /* triangle tests                                (collect_counters) */
-    uint64_t hits;          /* in-range primitive hits found                 (collect_counters) */
-    uint64_t shades;        /* non-terminal hits (scatter)                   (collect_counters) */
-    uint64_t emissive;      /* paths ended on an emitter                     (collect_counters) */
-    uint64_t sky;           /* paths ended on the sky                        (collect_counters) */
-    uint64_t active_lane_iters; /* sum over trace-loop trips of active lanes (collect_counters) */
-    uint64_t total_lane_iters;  /* 32 * warp-level trace-loop trips          (collect_counters) */
-    float kernel_ms;        /* device time of the render kernel(s), CUDA events on the ctx stream */
+    uint64_t sphere_hits;   /* ... that produced an in-range root */
+    uint64_t tri_tests;     /* triangle tests */
+    uint64_t tri_stage[3];  /* tests that passed the determinant / u / v checks (mesh.rs:127,140,150) */
+    uint64_t tri_hits;      /* in-range triangle hits */
+    uint64_t shades_sphere; /* non-terminal hits (scatter) on spheres */
+    uint64_t shades_tri;    /* ... on triangles */
+    uint64_t emissive;      /* paths ended on an emitter */
+    uint64_t sky;           /* paths ended on the sky */
+    uint64_t active_lane_iters; /* sum over nearest-hit queries of participating lanes */
+    uint64_t total_lane_iters;  /* 32 * warp-level query trips: ratio = SIMT efficiency at query level */
+    float kernel_ms;        /* device time of the render kernel, CUDA events on the ctx stream */
     float total_ms;         /* host wall time of the call, copies included */
     uint32_t intersector_used; /* rt_intersector actually run */
     uint32_t kernel_launches;  /* kernels launched by the call */
+    uint32_t grid_ctas, cta_threads, ctas_per_sm, scene_in_smem; /* launch shape of the render kernel */
+    uint32_t dyn_smem_bytes, reserved0;
 } rt_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------- */
 int rt_abi_version(void);
+/* sizeof(rt_sphere), sizeof(rt_triangle), sizeof(rt_params), sizeof(rt_stats) as compiled: lets a
+ * binding check its struct layouts at load time. */
+void rt_struct_sizes(size_t out[4]);
 /* Create a context on CUDA device `device` (one stream, one event pair). */
 int rt_init(int device, rt_ctx** out);
 void rt_shutdown(rt_ctx* ctx);
@@ -126,6 +135,13 @@ void rt_scene_destroy(rt_ctx* ctx, rt_scene* scene);
 /* BVH facts for tests / tooling: node count (2n-1 like bvh_impl.rs), depth, and the DFS leaf rank of every
  * primitive in world order (rank_out nullable, n entries). */
 int rt_scene_info(const rt_scene* scene, uint32_t* n_prims, uint32_t* n_nodes, uint32_t* depth, uint32_t* rank_out);
+/* Bytes rt_scene_create copied host→device for this scene (primitive SoA + BVH nodes + materials). */
+size_t rt_scene_device_bytes(const rt_scene* scene);
+
+/* Host-only BVH build (no GPU needed): the DFS leaf rank of every primitive in world order, as
+ * rt_scene_create computes it. For tests and tooling. Outputs nullable. */
+int rt_bvh_build_host(const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles, uint32_t n_triangles,
+                      const uint32_t* world_index, uint32_t* rank_out, uint32_t* n_nodes, uint32_t* depth);
 
 /* ---- render: replaces main.rs:53-83 -------------------------------------------------------------- */
 /* Renders band `division_no` into host memory: (height/divisions) rows * width * 3 bytes, RGB, row 0 =

@@ -62,6 +62,13 @@ extern "C" {
 
 int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
 
+void rt_struct_sizes(size_t out[4]) {
+    out[0] = sizeof(rt_sphere);
+    out[1] = sizeof(rt_triangle);
+    out[2] = sizeof(rt_params);
+    out[3] = sizeof(rt_stats);
+}
+
 const char* rt_last_error(const rt_ctx* ctx) { return ctx ? ctx->err.c_str() : g_init_err.c_str(); }
 
 int rt_init(int device, rt_ctx** out) {
@@ -162,6 +169,90 @@ inline bool finite3(const float* v) { return std::isfinite(v[0]) && std::isfinit
 
 }  // namespace
 
+
+// World order + bounds + BVH, shared by rt_scene_create and rt_bvh_build_host.  Host only.
+static int build_world_bvh(const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles,
+                           uint32_t n_triangles, const uint32_t* world_index, std::vector<PrimRef>* world_out,
+                           HostBVH* bvh, std::string* err) {
+    char buf[256];
+    const uint32_t n = n_spheres + n_triangles;
+    std::vector<PrimRef>& world = *world_out;
+    world.assign(n, PrimRef{0, 0});
+    {
+        std::vector<uint8_t> seen(n, 0);
+        for (uint32_t i = 0; i < n; i++) {
+            uint32_t pos = world_index ? world_index[i] : i;
+            if (pos >= n || seen[pos]) {
+                snprintf(buf, sizeof buf, "world_index is not a permutation of 0..%u", n - 1);
+                *err = buf;
+                return RT_ERR_INVALID_ARG;
+            }
+            seen[pos] = 1;
+            world[pos] = i < n_spheres ? PrimRef{0, i} : PrimRef{1, i - n_spheres};
+        }
+    }
+    // bounds per world position (Sphere::aabb sphere.rs:65-72, Triangle::aabb mesh.rs:46-95)
+    std::vector<Box> boxes(n);
+    for (uint32_t w = 0; w < n; w++) {
+        Box& b = boxes[w];
+        if (world[w].kind == 0) {
+            const rt_sphere& s = spheres[world[w].idx];
+            if (!finite3(s.center) || !std::isfinite(s.radius)) {
+                snprintf(buf, sizeof buf, "sphere %u has non-finite geometry", world[w].idx);
+                *err = buf;
+                return RT_ERR_BVH;
+            }
+            for (int a = 0; a < 3; a++) {
+                b.min[a] = s.center[a] - s.radius;
+                b.max[a] = s.center[a] + s.radius;
+            }
+        } else {
+            const rt_triangle& t = triangles[world[w].idx];
+            if (!finite3(t.a) || !finite3(t.b) || !finite3(t.c)) {
+                snprintf(buf, sizeof buf, "triangle %u has non-finite geometry", world[w].idx);
+                *err = buf;
+                return RT_ERR_BVH;
+            }
+            for (int a = 0; a < 3; a++) {
+                b.min[a] = ref_min(ref_min(t.a[a], t.c[a]), t.b[a]);
+                b.max[a] = ref_max(ref_max(t.a[a], t.c[a]), t.b[a]);
+            }
+        }
+    }
+    std::string berr;
+    if (!build_bvh(boxes, bvh, &berr)) {
+        *err = "BVH build failed: " + berr;
+        return RT_ERR_BVH;
+    }
+    if (bvh->depth > (uint32_t)MAX_STACK) {
+        snprintf(buf, sizeof buf, "BVH depth %u exceeds the traversal stack (%d)", bvh->depth, MAX_STACK);
+        *err = buf;
+        return RT_ERR_UNSUPPORTED;
+    }
+    return RT_OK;
+}
+
+int rt_bvh_build_host(const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles, uint32_t n_triangles,
+                      const uint32_t* world_index, uint32_t* rank_out, uint32_t* n_nodes, uint32_t* depth) {
+    const uint64_t n64 = (uint64_t)n_spheres + n_triangles;
+    if (n64 == 0) return RT_ERR_EMPTY_SCENE;
+    if (n64 > 0x3fffffffu) return RT_ERR_UNSUPPORTED;
+    if ((n_spheres && !spheres) || (n_triangles && !triangles)) return RT_ERR_INVALID_ARG;
+    std::vector<PrimRef> world;
+    HostBVH bvh;
+    std::string err;
+    int rc = build_world_bvh(spheres, n_spheres, triangles, n_triangles, world_index, &world, &bvh, &err);
+    if (rc) {
+        g_init_err = err;
+        return rc;
+    }
+    if (rank_out)
+        for (uint32_t r = 0; r < (uint32_t)n64; r++) rank_out[bvh.leaf_order[r]] = r;
+    if (n_nodes) *n_nodes = bvh.node_count;
+    if (depth) *depth = bvh.depth;
+    return RT_OK;
+}
+
 int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles,
                     uint32_t n_triangles, const uint32_t* world_index, rt_scene** out) {
     if (!ctx) return RT_ERR_INVALID_ARG;
@@ -175,47 +266,13 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     if ((n_spheres && !spheres) || (n_triangles && !triangles))
         return set_err(ctx, RT_ERR_INVALID_ARG, "rt_scene_create: NULL primitive array");
     const uint32_t n = (uint32_t)n64;
-
-    // world order
-    std::vector<PrimRef> world(n);
-    {
-        std::vector<uint8_t> seen(n, 0);
-        for (uint32_t i = 0; i < n; i++) {
-            uint32_t pos = world_index ? world_index[i] : i;
-            if (pos >= n || seen[pos])
-                return set_err(ctx, RT_ERR_INVALID_ARG, "world_index is not a permutation of 0..%u", n - 1);
-            seen[pos] = 1;
-            world[pos] = i < n_spheres ? PrimRef{0, i} : PrimRef{1, i - n_spheres};
-        }
-    }
-    // bounds per world position (Sphere::aabb sphere.rs:65-72, Triangle::aabb mesh.rs:46-95)
-    std::vector<Box> boxes(n);
-    for (uint32_t w = 0; w < n; w++) {
-        Box& b = boxes[w];
-        if (world[w].kind == 0) {
-            const rt_sphere& s = spheres[world[w].idx];
-            if (!finite3(s.center) || !std::isfinite(s.radius))
-                return set_err(ctx, RT_ERR_BVH, "sphere %u has non-finite geometry", world[w].idx);
-            for (int a = 0; a < 3; a++) {
-                b.min[a] = s.center[a] - s.radius;
-                b.max[a] = s.center[a] + s.radius;
-            }
-        } else {
-            const rt_triangle& t = triangles[world[w].idx];
-            if (!finite3(t.a) || !finite3(t.b) || !finite3(t.c))
-                return set_err(ctx, RT_ERR_BVH, "triangle %u has non-finite geometry", world[w].idx);
-            for (int a = 0; a < 3; a++) {
-                b.min[a] = ref_min(ref_min(t.a[a], t.c[a]), t.b[a]);
-                b.max[a] = ref_max(ref_max(t.a[a], t.c[a]), t.b[a]);
-            }
-        }
-    }
+    std::vector<PrimRef> world;
     HostBVH bvh;
-    std::string berr;
-    if (!build_bvh(boxes, &bvh, &berr)) return set_err(ctx, RT_ERR_BVH, "BVH build failed: %s", berr.c_str());
-    if (bvh.depth > (uint32_t)MAX_STACK)
-        return set_err(ctx, RT_ERR_UNSUPPORTED, "BVH depth %u exceeds the traversal stack (%d)", bvh.depth, MAX_STACK);
-
+    {
+        std::string herr;
+        int hrc = build_world_bvh(spheres, n_spheres, triangles, n_triangles, world_index, &world, &bvh, &herr);
+        if (hrc) return set_err(ctx, hrc, "%s", herr.c_str());
+    }
     // pids: spheres then triangles, each in DFS leaf order
     std::vector<uint32_t> pid_of_world(n), rank_of_world(n);
     uint32_t next_s = 0, next_t = n_spheres;
@@ -368,6 +425,8 @@ int rt_scene_info(const rt_scene* scene, uint32_t* n_prims, uint32_t* n_nodes, u
     return RT_OK;
 }
 
+size_t rt_scene_device_bytes(const rt_scene* scene) { return scene ? scene->blob_bytes : 0; }
+
 // -------------------------------------------------------------------------------------------------
 // Render
 // -------------------------------------------------------------------------------------------------
@@ -467,7 +526,7 @@ int launch(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, uint32_t row0,
 }
 
 int finish_stats(rt_ctx* ctx, const Resolved& r, uint64_t pixels, rt_stats* st,
-                 std::chrono::steady_clock::time_point t0) {
+                 std::chrono::steady_clock::time_point t0, const LaunchInfo& li) {
     if (!st) return RT_OK;
     CK(ctx, cudaMemcpyAsync(ctx->h_ctr, ctx->d_ctr, NUM_COUNTERS * sizeof(unsigned long long), cudaMemcpyDeviceToHost,
                             ctx->stream));
@@ -479,9 +538,14 @@ int finish_stats(rt_ctx* ctx, const Resolved& r, uint64_t pixels, rt_stats* st,
     st->slab_tests = c[CTR_SLAB];
     st->sphere_tests = c[CTR_SPH_TEST];
     st->sphere_exact = c[CTR_SPH_EXACT];
+    st->sphere_hits = c[CTR_SPH_HIT];
     st->tri_tests = c[CTR_TRI_TEST];
-    st->hits = c[CTR_HITS];
-    st->shades = c[CTR_SHADES];
+    st->tri_stage[0] = c[CTR_TRI_S1];
+    st->tri_stage[1] = c[CTR_TRI_S2];
+    st->tri_stage[2] = c[CTR_TRI_S3];
+    st->tri_hits = c[CTR_TRI_HIT];
+    st->shades_sphere = c[CTR_SHADE_SPH];
+    st->shades_tri = c[CTR_SHADE_TRI];
     st->emissive = c[CTR_EMISSIVE];
     st->sky = c[CTR_SKY];
     st->active_lane_iters = c[CTR_ACTIVE_LANES];
@@ -492,6 +556,11 @@ int finish_stats(rt_ctx* ctx, const Resolved& r, uint64_t pixels, rt_stats* st,
     st->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     st->intersector_used = (uint32_t)r.isect;
     st->kernel_launches = 1;
+    st->grid_ctas = li.grid;
+    st->cta_threads = li.threads;
+    st->ctas_per_sm = (uint32_t)li.ctas_per_sm;
+    st->scene_in_smem = li.scene_in_smem ? 1u : 0u;
+    st->dyn_smem_bytes = (uint32_t)li.dyn_smem;
     return RT_OK;
 }
 
@@ -506,11 +575,12 @@ int render_rows_to_host(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, u
     CK(ctx, cudaSetDevice(ctx->device));
     int rc = ensure_out(ctx, bytes);
     if (rc) return rc;
-    rc = launch(ctx, scene, r, row0, row1, 0, 1, ctx->d_out, row0, nullptr);
+    LaunchInfo li;
+    rc = launch(ctx, scene, r, row0, row1, 0, 1, ctx->d_out, row0, &li);
     if (rc) return rc;
     CK(ctx, cudaMemcpyAsync(out_rgb, ctx->d_out, bytes, cudaMemcpyDeviceToHost, ctx->stream));
     CK(ctx, cudaStreamSynchronize(ctx->stream));
-    return finish_stats(ctx, r, (uint64_t)(row1 - row0) * r.p.width, stats, t0);
+    return finish_stats(ctx, r, (uint64_t)(row1 - row0) * r.p.width, stats, t0, li);
 }
 
 }  // namespace
@@ -555,12 +625,13 @@ int rt_render_tiles_device(rt_ctx* ctx, const rt_scene* scene, const rt_params* 
     if (!frame_dev) return set_err(ctx, RT_ERR_INVALID_ARG, "frame_dev is NULL");
     if (tile_ranks == 0 || tile_rank >= tile_ranks) return set_err(ctx, RT_ERR_INVALID_ARG, "bad tile_rank/tile_ranks");
     CK(ctx, cudaSetDevice(ctx->device));
-    rc = launch(ctx, scene, r, 0, r.p.height, tile_rank, tile_ranks, (uint8_t*)frame_dev, 0, nullptr);
+    LaunchInfo li;
+    rc = launch(ctx, scene, r, 0, r.p.height, tile_rank, tile_ranks, (uint8_t*)frame_dev, 0, &li);
     if (rc) return rc;
     if (sync) {
         CK(ctx, cudaStreamSynchronize(ctx->stream));
         // pixel count of this rank's tiles is not needed by callers; report the frame total / ranks
-        return finish_stats(ctx, r, (uint64_t)r.p.width * r.p.height / tile_ranks, stats, t0);
+        return finish_stats(ctx, r, (uint64_t)r.p.width * r.p.height / tile_ranks, stats, t0, li);
     }
     return RT_OK;
 }

@@ -61,8 +61,8 @@ struct DevParams {
 };
 
 enum CounterSlot {
-    CTR_RAYS = 0, CTR_SLAB, CTR_SPH_TEST, CTR_SPH_EXACT, CTR_TRI_TEST, CTR_HITS, CTR_SHADES, CTR_EMISSIVE,
-    CTR_SKY, CTR_ACTIVE_LANES, CTR_TOTAL_LANES, NUM_COUNTERS
+    CTR_RAYS = 0, CTR_SLAB, CTR_SPH_TEST, CTR_SPH_EXACT, CTR_SPH_HIT, CTR_TRI_TEST, CTR_TRI_S1, CTR_TRI_S2, CTR_TRI_S3,
+    CTR_TRI_HIT, CTR_SHADE_SPH, CTR_SHADE_TRI, CTR_EMISSIVE, CTR_SKY, CTR_ACTIVE_LANES, CTR_TOTAL_LANES, NUM_COUNTERS
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -235,19 +235,24 @@ __device__ __forceinline__ bool sphere_root_exact(V3 d, V3 oc, float r2, float* 
     return false;
 }
 
-// Triangle::get_roots (mesh.rs:109-161), two-sided Moeller-Trumbore, + t-range (shapes/mod.rs:109-115)
-__device__ __forceinline__ bool triangle_root_exact(V3 o, V3 d, V3 a, V3 ab, V3 ac, float* t_out) {
+// Triangle::get_roots (mesh.rs:109-161), two-sided Moeller-Trumbore, + t-range (shapes/mod.rs:109-115).
+// *stage = number of rejection tests passed (0 det, 1 u, 2 v, 3 reached dist) for the FLOP accounting.
+__device__ __forceinline__ bool triangle_root_exact(V3 o, V3 d, V3 a, V3 ab, V3 ac, float* t_out, int* stage) {
     const float EPSILON = 0.00001f;
+    *stage = 0;
     V3 u_vec = x_cross(d, ac);
     float det = x_dot(ab, u_vec);
     if (det < EPSILON && det > -EPSILON) return false;
+    *stage = 1;
     float inv_det = x_div(1.0f, det);
     V3 ao = x_sub(o, a);
     float u = x_mul(x_dot(ao, u_vec), inv_det);
     if (!(u >= 0.0f && u <= 1.0f)) return false;
+    *stage = 2;
     V3 v_vec = x_cross(ao, ab);
     float v = x_mul(x_dot(d, v_vec), inv_det);
     if (v < 0.0f || x_add(u, v) > 1.0f) return false;
+    *stage = 3;
     float dist = x_mul(x_dot(ac, v_vec), inv_det);
     if (!(dist > EPSILON)) return false;
     if (!in_range(dist)) return false;

@@ -87,7 +87,7 @@ __device__ __forceinline__ void test_sphere(const DevScene& sc, const float4 s, 
     if (COUNT) ctr.v[CTR_SPH_EXACT]++;
     float t;
     if (!sphere_root_exact(d, oc, s.w, &t)) return;
-    if (COUNT) ctr.v[CTR_HITS]++;
+    if (COUNT) ctr.v[CTR_SPH_HIT]++;
     consider(sc, o, d, t, pid, best);
 }
 
@@ -99,8 +99,15 @@ __device__ __forceinline__ void test_triangle(const DevScene& sc, const float4* 
     V3 ac = ld3(tri[4 * tidx + 2]);
     if (COUNT) ctr.v[CTR_TRI_TEST]++;
     float t;
-    if (!triangle_root_exact(o, d, a, ab, ac, &t)) return;
-    if (COUNT) ctr.v[CTR_HITS]++;
+    int stage;
+    bool hit = triangle_root_exact(o, d, a, ab, ac, &t, &stage);
+    if (COUNT) {
+        if (stage >= 1) ctr.v[CTR_TRI_S1]++;
+        if (stage >= 2) ctr.v[CTR_TRI_S2]++;
+        if (stage >= 3) ctr.v[CTR_TRI_S3]++;
+        if (hit) ctr.v[CTR_TRI_HIT]++;
+    }
+    if (!hit) return;
     consider(sc, o, d, t, pid, best);
 }
 
@@ -306,8 +313,8 @@ __global__ void __launch_bounds__(THREADS) render_kernel(const DevScene sc, cons
                         done = true;
                         if (COUNT) ctr.v[CTR_EMISSIVE]++;
                     } else {
-                        if (COUNT) ctr.v[CTR_SHADES]++;
                         V3 n;
+                        if (COUNT) ctr.v[h.pid < (int)sc.ns ? CTR_SHADE_SPH : CTR_SHADE_TRI]++;
                         if (h.pid < (int)sc.ns) {
                             const float4 sp4 = sv.sph[h.pid];
                             n = x_normalize_or_zero(x_sub(h.p, ld3(sp4)));  // sphere.rs:49-51

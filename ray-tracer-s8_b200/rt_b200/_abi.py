@@ -40,15 +40,22 @@ class RtParams(C.Structure):
 class RtStats(C.Structure):
     _fields_ = [
         ("rays", C.c_uint64), ("primary", C.c_uint64), ("slab_tests", C.c_uint64), ("sphere_tests", C.c_uint64),
-        ("sphere_exact", C.c_uint64), ("tri_tests", C.c_uint64), ("hits", C.c_uint64), ("shades", C.c_uint64),
-        ("emissive", C.c_uint64), ("sky", C.c_uint64), ("active_lane_iters", C.c_uint64),
-        ("total_lane_iters", C.c_uint64),
+        ("sphere_exact", C.c_uint64), ("sphere_hits", C.c_uint64), ("tri_tests", C.c_uint64),
+        ("tri_stage", C.c_uint64 * 3), ("tri_hits", C.c_uint64), ("shades_sphere", C.c_uint64),
+        ("shades_tri", C.c_uint64), ("emissive", C.c_uint64), ("sky", C.c_uint64),
+        ("active_lane_iters", C.c_uint64), ("total_lane_iters", C.c_uint64),
         ("kernel_ms", C.c_float), ("total_ms", C.c_float),
         ("intersector_used", C.c_uint32), ("kernel_launches", C.c_uint32),
+        ("grid_ctas", C.c_uint32), ("cta_threads", C.c_uint32), ("ctas_per_sm", C.c_uint32),
+        ("scene_in_smem", C.c_uint32), ("dyn_smem_bytes", C.c_uint32), ("reserved0", C.c_uint32),
     ]
 
     def as_dict(self):
-        return {name: getattr(self, name) for name, _ in self._fields_}
+        d = {}
+        for name, _ in self._fields_:
+            v = getattr(self, name)
+            d[name] = list(v) if hasattr(v, "__len__") else v
+        return d
 
 
 # every symbol include/rt_b200.h declares (tests check that the library exports all of them)
@@ -56,7 +63,7 @@ EXPORTS = [
     "rt_abi_version", "rt_init", "rt_shutdown", "rt_last_error", "rt_scene_create", "rt_scene_destroy",
     "rt_scene_info", "rt_render_division", "rt_render_frame", "rt_render_tiles_device", "rt_sync", "rt_stream",
     "rt_host_alloc", "rt_host_free", "rt_frame_alloc", "rt_frame_open", "rt_frame_close", "rt_frame_free",
-    "rt_frame_download", "rt_measure_fp32_peak", "rt_device_info",
+    "rt_frame_download", "rt_measure_fp32_peak", "rt_device_info", "rt_bvh_build_host", "rt_struct_sizes", "rt_scene_device_bytes",
 ]
 
 _lib = None
@@ -120,5 +127,15 @@ def lib():
     L.rt_measure_fp32_peak.restype = i32
     L.rt_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.c_char_p]
     L.rt_device_info.restype = i32
+    L.rt_bvh_build_host.argtypes = [vp, u32, vp, u32, vp, vp, C.POINTER(u32), C.POINTER(u32)]
+    L.rt_bvh_build_host.restype = i32
+    L.rt_scene_device_bytes.argtypes = [vp]
+    L.rt_scene_device_bytes.restype = sz
+    L.rt_struct_sizes.argtypes = [C.POINTER(sz)]
+    L.rt_struct_sizes.restype = None
+    sizes = (sz * 4)()
+    L.rt_struct_sizes(sizes)
+    if list(sizes) != [36, 56, C.sizeof(RtParams), C.sizeof(RtStats)]:
+        raise RuntimeError(f"struct layout mismatch between librt_b200.so {list(sizes)} and this binding")
     _lib = L
     return L

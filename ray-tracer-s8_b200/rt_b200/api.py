@@ -41,6 +41,20 @@ def _ptr(a):
     return None if a is None or a.size == 0 else a.ctypes.data_as(C.c_void_p)
 
 
+def bvh_build_host(spheres=None, triangles=None, world_index=None):
+    """Host-only BVH build (no GPU): (rank per world position, node count, depth)."""
+    L = _abi.lib()
+    sp = np.ascontiguousarray(spheres if spheres is not None else np.zeros(0, SPHERE_DTYPE), dtype=SPHERE_DTYPE)
+    tr = np.ascontiguousarray(triangles if triangles is not None else np.zeros(0, TRIANGLE_DTYPE), dtype=TRIANGLE_DTYPE)
+    wi = None if world_index is None else np.ascontiguousarray(world_index, dtype=np.uint32)
+    rank = np.zeros(len(sp) + len(tr), dtype=np.uint32)
+    nn, d = C.c_uint32(), C.c_uint32()
+    rc = L.rt_bvh_build_host(_ptr(sp), len(sp), _ptr(tr), len(tr), _ptr(wi), _ptr(rank), C.byref(nn), C.byref(d))
+    if rc != 0:
+        raise RtError(rc, L.rt_last_error(None).decode())
+    return rank, nn.value, d.value
+
+
 class Context:
     """One GPU, one stream; single owner (same contract as the reference's single worker thread)."""
 
@@ -185,6 +199,10 @@ class Scene:
         rank = np.zeros(self.n_spheres + self.n_triangles, dtype=np.uint32)
         self._ctx._check(self._ctx._lib.rt_scene_info(self._h, C.byref(n), C.byref(nn), C.byref(d), _ptr(rank)))
         return {"n_prims": n.value, "n_nodes": nn.value, "depth": d.value, "rank": rank}
+
+    @property
+    def device_bytes(self) -> int:
+        return int(self._ctx._lib.rt_scene_device_bytes(self._h))
 
     def close(self):
         if self._h and self._ctx._h:

@@ -1,0 +1,332 @@
+"""GPU: the CUDA path through the C ABI against the oracle on the same seeded inputs.
+
+Bar (BASELINE.json north_star): every 8-bit channel within +-1 LSB on >= 99.9 % of pixels and PSNR >= 50 dB.
+This implementation is built to be bit-exact (exact-arithmetic domain in csrc/rt_device.cuh), so the tests
+additionally assert zero differing bytes wherever the oracle's BVH and brute force agree.
+"""
+import json
+import threading
+import urllib.error
+import urllib.request
+from http.server import BaseHTTPRequestHandler, HTTPServer
+
+import numpy as np
+import pytest
+
+from conftest import assert_parity, frame_compare
+
+pytestmark = pytest.mark.gpu
+
+BOTH = [1, 2]  # RT_INTERSECT_BRUTE, RT_INTERSECT_BVH
+
+
+def _render(ctx, rt, sp, tr, w, h, spp, mb, isect=0, seed=0, wi=None, **cam):
+    sc = ctx.scene(sp, tr, wi)
+    try:
+        p = rt.make_params(w, h, spp=spp, max_bounces=mb, seed=seed, intersector=isect, **cam)
+        return ctx.render_frame(sc, p, want_stats=True)
+    finally:
+        sc.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# parity against the oracle at sizes the oracle finishes in seconds
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("isect", BOTH)
+def test_c1_full_size(ctx, rt, O, isect):
+    """BASELINE config 1: 640x480, 1 spp, reference default depth (max_bounces 10), 64 spheres."""
+    c = rt.scenes.CONFIGS["C1"]
+    sp, tr = rt.scenes.config_scene("C1")
+    ref, ost = O.render_frame(sp, tr, c["width"], c["height"], c["spp"], c["max_bounces"], want_stats=True)
+    img, st = _render(ctx, rt, sp, tr, c["width"], c["height"], c["spp"], c["max_bounces"], isect)
+    assert_parity(img, ref)
+    assert st["rays"] == ost["rays"] and st["primary"] == ost["primary"]
+    assert st["intersector_used"] == isect and st["kernel_launches"] == 1
+
+
+@pytest.mark.parametrize("isect", BOTH)
+def test_c2_scene_bands(ctx, rt, O, isect):
+    """BASELINE config 2 (1920x1080, 1 spp, depth 5, 256 spheres): three of the controller's 20 bands."""
+    c = rt.scenes.CONFIGS["C2"]
+    sp, tr = rt.scenes.config_scene("C2")
+    sc = ctx.scene(sp, tr)
+    for d in (0, 9, 19):
+        po = O.make_params(c["width"], c["height"], 20, d, c["spp"], c["max_bounces"])
+        ref, _ = O.render_rows(sp, tr, po)
+        p = rt.make_params(c["width"], c["height"], divisions=20, division_no=d, spp=c["spp"],
+                           max_bounces=c["max_bounces"], intersector=isect)
+        img = ctx.render_division(sc, p)
+        assert img.shape == (54, 1920, 3)
+        assert_parity(img, ref)
+    sc.close()
+
+
+def test_c3_scene_crop(ctx, rt, O):
+    """BASELINE config 3 scene (1024 spheres + plane, 16 spp, depth 5) on a 4K band (rows 1080..1095)."""
+    c = rt.scenes.CONFIGS["C3"]
+    sp, tr = rt.scenes.config_scene("C3")
+    div = c["height"] // 16
+    d = 1080 // 16
+    ref, ost = O.render_rows(sp, tr, O.make_params(c["width"], c["height"], div, d, c["spp"], c["max_bounces"]),
+                             want_stats=True)
+    sc = ctx.scene(sp, tr)
+    p = rt.make_params(c["width"], c["height"], divisions=div, division_no=d, spp=c["spp"],
+                       max_bounces=c["max_bounces"])
+    img, st = ctx.render_division(sc, p, want_stats=True)
+    sc.close()
+    assert_parity(img, ref)
+    assert st["rays"] == ost["rays"]
+
+
+@pytest.mark.parametrize("isect", BOTH)
+@pytest.mark.parametrize("case", [
+    dict(n=1, plane=False, w=128, h=96, spp=2, mb=5),        # root of the BVH is a leaf
+    dict(n=2, plane=False, w=64, h=64, spp=3, mb=1),
+    dict(n=0, plane=True, w=128, h=96, spp=2, mb=5),         # triangles only
+    dict(n=32, plane=True, w=101, h=67, spp=3, mb=4),        # ragged size: partial tiles, unaligned rows
+    dict(n=300, plane=True, w=7, h=5, spp=5, mb=6),          # frame smaller than one tile
+    dict(n=150, plane=False, w=256, h=8, spp=1, mb=12),
+    dict(n=96, plane=True, w=64, h=64, spp=2, mb=62),        # deepest path this build supports
+])
+def test_edge_cases(ctx, rt, O, isect, case):
+    sp = rt.scenes.synthetic_spheres(case["n"], 17) if case["n"] else None
+    tr = rt.scenes.ground_plane() if case["plane"] else None
+    ref, ost = O.render_frame(sp, tr, case["w"], case["h"], case["spp"], case["mb"], seed=5, want_stats=True)
+    img, st = _render(ctx, rt, sp, tr, case["w"], case["h"], case["spp"], case["mb"], isect, seed=5)
+    assert_parity(img, ref)
+    assert st["rays"] == ost["rays"]
+
+
+@pytest.mark.parametrize("isect", BOTH)
+def test_mixed_world_order_and_mesh(ctx, rt, O, isect):
+    """Spheres and triangles interleaved in the world, plus a small closed mesh (shared edges)."""
+    sc = rt.scenes
+    sp = sc.synthetic_spheres(40, 21)
+    # an octahedron around (0,0,-6): 8 triangles sharing edges and vertices
+    v = np.array([[1, 0, 0], [-1, 0, 0], [0, 1, 0], [0, -1, 0], [0, 0, 1], [0, 0, -1]], dtype=np.float32) * 1.5
+    v += np.array([0, 0, -6], dtype=np.float32)
+    faces = [(0, 2, 4), (2, 1, 4), (1, 3, 4), (3, 0, 4), (2, 0, 5), (1, 2, 5), (3, 1, 5), (0, 3, 5)]
+    tr = np.zeros(len(faces) + 2, dtype=sc.TRIANGLE_DTYPE)
+    for i, (a, b, c) in enumerate(faces):
+        tr[i] = (v[a], v[b], v[c], (0.8, 0.6, 0.3), 0.3 * (i % 3), 0.0)
+    tr[len(faces):] = sc.ground_plane()
+    wi = np.random.default_rng(3).permutation(len(sp) + len(tr)).astype(np.uint32)
+    ref, ost = O.render_frame(sp, tr, 160, 120, 4, 6, seed=9, world_index=wi, want_stats=True)
+    img, st = _render(ctx, rt, sp, tr, 160, 120, 4, 6, isect, seed=9, wi=wi)
+    assert_parity(img, ref)
+    assert st["rays"] == ost["rays"]
+
+
+def test_camera_parameters_and_seeds(ctx, rt, O):
+    sp, tr = rt.scenes.synthetic_spheres(64, 2), rt.scenes.ground_plane()
+    cam = dict(cam_origin=(0.5, 0.25, 1.0), aperture=0.02, focus_distance=6.0, field_of_view=1.0, focal_length=1.5)
+    for seed in (0, 1, 2**63 + 12345, 2**64 - 1):
+        ref, _ = O.render_frame(sp, tr, 96, 64, 3, 4, seed=seed, **cam)
+        img, _ = _render(ctx, rt, sp, tr, 96, 64, 3, 4, 0, seed=seed, **cam)
+        assert_parity(img, ref)
+
+
+def test_reference_defaults(ctx, rt, O):
+    """Zero params = the reference's literals: 100 spp, max_bounces 10, aperture 0.1, fov PI/2 (main.rs:39-51)."""
+    sp = rt.scenes.synthetic_spheres(16, 4)
+    ref, ost = O.render_frame(sp, None, 32, 24, 0, 0, want_stats=True)
+    img, st = _render(ctx, rt, sp, None, 32, 24, 0, 0)
+    assert_parity(img, ref)
+    assert st["primary"] == 32 * 24 * 100 and st["rays"] == ost["rays"]
+
+
+@pytest.mark.parametrize("isect", BOTH)
+def test_golden_frames(ctx, rt, isect):
+    import golden.make_golden as G
+
+    for name, case in G.CASES.items():
+        sp, tr = G.scene_of(rt.scenes, case)
+        img, _ = _render(ctx, rt, sp, tr, case["w"], case["h"], case["spp"], case["mb"], isect, seed=case["seed"])
+        assert_parity(img, G.load(name))
+
+
+def test_counters_match_oracle(ctx, rt, O):
+    """The instrumented kernel's path-level counters equal the oracle's for the same seed."""
+    sp, tr = rt.scenes.synthetic_spheres(128, 8), rt.scenes.ground_plane()
+    _, ost = O.render_frame(sp, tr, 128, 72, 4, 5, want_stats=True)
+    sc = ctx.scene(sp, tr)
+    for isect in BOTH:
+        p = rt.make_params(128, 72, spp=4, max_bounces=5, intersector=isect, collect_counters=True)
+        img, st = ctx.render_frame(sc, p, want_stats=True)
+        p.collect_counters = 0
+        img2, st2 = ctx.render_frame(sc, p, want_stats=True)
+        assert np.array_equal(img, img2) and st["rays"] == st2["rays"] == ost["rays"]
+        assert st["shades_sphere"] == ost["shades_sphere"] and st["shades_tri"] == ost["shades_tri"]
+        assert st["emissive"] == ost["emissive"] and st["sky"] == ost["sky"]
+        assert st["active_lane_iters"] == st["rays"] and st["total_lane_iters"] >= st["rays"]
+        if isect == 1:
+            assert st["sphere_tests"] == st["rays"] * 128 and st["tri_tests"] == st["rays"] * 2
+        else:
+            assert 0 < st["slab_tests"] and st["sphere_tests"] < st["rays"] * 128
+    _, ob = O.render_frame(sp, tr, 128, 72, 4, 5, mode=1, want_stats=True)
+    p = rt.make_params(128, 72, spp=4, max_bounces=5, intersector=1, collect_counters=True)
+    _, st = ctx.render_frame(sc, p, want_stats=True)
+    assert st["tri_tests"] == ob["tri_tests"] and st["sphere_tests"] == ob["sphere_tests"]
+    assert st["tri_stage"] == [ob["tri_tests"] - ob["tri_exit"][0], ob["tri_tests"] - ob["tri_exit"][0] - ob["tri_exit"][1],
+                               ob["tri_exit"][3]]
+    assert st["sphere_hits"] == ob["sphere_hits"] and st["tri_hits"] == ob["tri_hits"]
+    sc.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# size-independent properties at BASELINE's full sizes
+# ---------------------------------------------------------------------------------------------------
+def test_c2_full_size_properties(ctx, rt):
+    """Full 1920x1080: determinism, intersector independence, division partition == whole frame."""
+    c = rt.scenes.CONFIGS["C2"]
+    sp, tr = rt.scenes.config_scene("C2")
+    sc = ctx.scene(sp, tr)
+    kw = dict(spp=c["spp"], max_bounces=c["max_bounces"])
+    a, sa = ctx.render_frame(sc, rt.make_params(c["width"], c["height"], intersector=2, **kw), want_stats=True)
+    b, sb = ctx.render_frame(sc, rt.make_params(c["width"], c["height"], intersector=2, **kw), want_stats=True)
+    k1, s1 = ctx.render_frame(sc, rt.make_params(c["width"], c["height"], intersector=1, **kw), want_stats=True)
+    assert np.array_equal(a, b) and np.array_equal(a, k1)
+    assert sa["rays"] == sb["rays"] == s1["rays"] and sa["primary"] == 1920 * 1080
+    bands = [ctx.render_division(sc, rt.make_params(c["width"], c["height"], divisions=20, division_no=d, **kw))
+             for d in range(20)]
+    assert np.array_equal(np.concatenate(bands, axis=0), a)
+    # the sky saturates the u8 cast above the horizon (main.rs:136: t = y*0.5 + 1 > 1)
+    assert (a[:400] == 255).mean() > 0.9
+    sc.close()
+
+
+def test_c3_full_size_tile_partition(ctx, rt):
+    """Full 3840x2160 (4 spp to bound the time): 3 emulated ranks rendering their tiles into one frame
+    reproduce the single-rank frame; ray counts add up."""
+    c = rt.scenes.CONFIGS["C3"]
+    sp, tr = rt.scenes.config_scene("C3")
+    sc = ctx.scene(sp, tr)
+    p = rt.make_params(c["width"], c["height"], spp=4, max_bounces=c["max_bounces"])
+    whole, sw = ctx.render_frame(sc, p, want_stats=True)
+    nbytes = c["width"] * c["height"] * 3
+    dev, _ = ctx.frame_alloc(nbytes)
+    rays = 0
+    for r in range(3):
+        st = ctx.render_tiles_device(sc, p, r, 3, dev, sync=True, want_stats=True)
+        rays += st["rays"]
+    out = np.zeros((c["height"], c["width"], 3), dtype=np.uint8)
+    ctx.frame_download(dev, out)
+    ctx.frame_free(dev)
+    sc.close()
+    assert np.array_equal(out, whole) and rays == sw["rays"]
+
+
+# ---------------------------------------------------------------------------------------------------
+# boundary behaviour (include/rt_b200.h)
+# ---------------------------------------------------------------------------------------------------
+def test_error_codes(ctx, rt):
+    sp = rt.scenes.synthetic_spheres(4)
+    with pytest.raises(rt.RtError) as e:
+        ctx.scene(None, None)
+    assert e.value.status == -2 and "never terminates" in e.value.message
+    sc = ctx.scene(sp, None)
+    with pytest.raises(rt.RtError) as e:
+        ctx.render_frame(sc, rt.make_params(16, 9, divisions=2, spp=1, max_bounces=1))
+    assert e.value.status == -1 and "multiple of divisions" in e.value.message
+    with pytest.raises(rt.RtError) as e:
+        ctx.render_frame(sc, rt.make_params(16, 8, spp=1, max_bounces=1), out=np.zeros((8, 16, 2), dtype=np.uint8))
+    assert e.value.status == -1 and "out_len" in e.value.message
+    with pytest.raises(rt.RtError) as e:
+        ctx.render_frame(sc, rt.make_params(16, 8, spp=1, max_bounces=64))
+    assert e.value.status == -6
+    with pytest.raises(rt.RtError) as e:
+        ctx.render_division(sc, rt.make_params(16, 8, divisions=2, division_no=2, spp=1, max_bounces=1))
+    assert e.value.status == -1
+    # the context stays usable after errors
+    img = ctx.render_frame(sc, rt.make_params(16, 8, spp=1, max_bounces=1))
+    assert img.shape == (8, 16, 3)
+    sc.close()
+
+
+def test_pinned_output_buffer(ctx, rt, O):
+    sp = rt.scenes.synthetic_spheres(16, 4)
+    buf = ctx.pinned_empty((48, 64, 3))
+    sc = ctx.scene(sp, None)
+    ctx.render_frame(sc, rt.make_params(64, 48, spp=2, max_bounces=3), out=buf)
+    sc.close()
+    ref, _ = O.render_frame(sp, None, 64, 48, 2, 3)
+    assert_parity(buf, ref)
+
+
+def test_fp32_peak_probe(ctx):
+    tf, ms = ctx.measure_fp32_peak()
+    assert 30.0 < tf < 90.0 and ms > 0       # nominal 148 SM x 128 lanes x 2 x 1.965 GHz = 74.5 TFLOP/s
+
+
+# ---------------------------------------------------------------------------------------------------
+# the slave's interface on top of the GPU path (ray-tracer-slave/src/main.rs:32-106,148-174)
+# ---------------------------------------------------------------------------------------------------
+def test_worker_render_info_to_image_slice(rt, O):
+    from rt_b200 import slave, wire
+
+    sp, tr = rt.scenes.synthetic_spheres(48, 6), rt.scenes.ground_plane()
+    wi = np.random.default_rng(1).permutation(50).astype(np.uint32)
+    meta = wire.RenderMeta(60, 80, 5, "123e4567-e89b-12d3-a456-426614174000")
+    wk = slave.Worker(0, spp=3, max_bounces=4, seed=2)
+    try:
+        for d in (0, 3, 4):
+            body = wire.render_info_to_json(sp, tr, meta, d, wi)
+            sl = wire.ImageSlice.from_json(wk.render_json(body))
+            assert sl.division_no == d and sl.id == meta.id and sl.image.size == 12 * 80 * 3
+            ref, _ = O.render_rows(sp, tr, O.make_params(80, 60, 5, d, 3, 4, 2), world_index=wi)
+            assert_parity(sl.image.reshape(12, 80, 3), ref)
+        assert wk.scene_uploads == 1          # one upload + BVH build per job id, not per division
+    finally:
+        wk.close()
+
+
+def test_http_shell_end_to_end(rt, O):
+    """POST / → ack text → the slave POSTs the ImageSlice to the master's /result (fake master here)."""
+    from rt_b200 import slave, wire
+
+    got = {}
+    done = threading.Event()
+
+    class Master(BaseHTTPRequestHandler):
+        def do_POST(self):  # noqa: N802
+            n = int(self.headers["Content-Length"])
+            got["path"], got["body"] = self.path, self.rfile.read(n)
+            self.send_response(200)
+            self.send_header("Content-Length", "2")
+            self.end_headers()
+            self.wfile.write(b"ok")
+            done.set()
+
+        def log_message(self, *a):
+            pass
+
+    master = HTTPServer(("127.0.0.1", 0), Master)
+    threading.Thread(target=master.serve_forever, daemon=True).start()
+    ready, stop = threading.Event(), threading.Event()
+    wk = slave.Worker(0, spp=2, max_bounces=3)
+    t = threading.Thread(target=slave.serve, kwargs=dict(
+        host="127.0.0.1", port=0, result_url=f"http://127.0.0.1:{master.server_address[1]}/result", worker=wk,
+        ready=ready, stop=stop), daemon=True)
+    t.start()
+    assert ready.wait(30)
+    sp = rt.scenes.synthetic_spheres(20, 3)
+    meta = wire.RenderMeta(32, 48, 4, "00000000-0000-4000-8000-000000000001")
+    req = urllib.request.Request(f"http://127.0.0.1:{ready.port}/", data=wire.render_info_to_json(sp, None, meta, 2).encode(),
+                                 headers={"Content-Type": "application/json"}, method="POST")
+    with urllib.request.urlopen(req, timeout=30) as r:
+        assert r.status == 200 and r.read().decode() == slave.ACK_TEXT
+    # a malformed body is a 400, like actix's Json extractor
+    bad = urllib.request.Request(f"http://127.0.0.1:{ready.port}/", data=b"{}", method="POST")
+    with pytest.raises(urllib.error.HTTPError) as he:
+        urllib.request.urlopen(bad, timeout=30)
+    assert he.value.code == 400
+    assert done.wait(60)
+    stop.set()
+    t.join(30)
+    master.shutdown()
+    wk.close()
+    assert got["path"] == "/result"
+    o = json.loads(got["body"])
+    assert list(o.keys()) == ["division_no", "image", "id"] and o["division_no"] == 2 and o["id"] == meta.id
+    ref, _ = O.render_rows(sp, None, O.make_params(48, 32, 4, 2, 2, 3))
+    assert_parity(np.array(o["image"], dtype=np.uint8).reshape(8, 48, 3), ref)

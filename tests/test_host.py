@@ -1,0 +1,216 @@
+"""CPU: the C-ABI library loads and exports what include/rt_b200.h declares; host-side logic
+(BVH build, scenes, wire types, tile partition, gloo world_size-2 assembly).  No compute calls."""
+import json
+import os
+import re
+import socket
+
+import numpy as np
+import pytest
+
+ROOT = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+
+
+def test_library_exports_every_declared_symbol(rt):
+    from rt_b200 import _abi
+
+    L = _abi.lib()
+    header = open(os.path.join(ROOT, "include", "rt_b200.h")).read()
+    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+    declared = set(re.findall(r"\b(rt_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
+    for name in declared:
+        assert hasattr(L, name), name
+    assert L.rt_abi_version() == 1
+
+
+def test_struct_layouts_match_header(rt):
+    import ctypes as C
+
+    from rt_b200 import _abi, scenes
+
+    assert scenes.SPHERE_DTYPE.itemsize == 36 and scenes.TRIANGLE_DTYPE.itemsize == 56
+    sizes = (C.c_size_t * 4)()
+    _abi.lib().rt_struct_sizes(sizes)
+    assert list(sizes) == [36, 56, C.sizeof(_abi.RtParams), C.sizeof(_abi.RtStats)]
+
+
+def test_no_device_fails_loudly(rt):
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("a CUDA device is present")
+    with pytest.raises(rt.RtError) as e:
+        rt.Context(0)
+    assert e.value.status == -3 and "no CPU fallback" in e.value.message
+
+
+def test_host_bvh_matches_reference_leaf_order(O, rt):
+    from rt_b200 import api, scenes
+
+    rng = np.random.default_rng(5)
+    for n, plane in [(1, False), (2, False), (3, True), (64, False), (257, True), (1024, True)]:
+        sp = scenes.synthetic_spheres(n, n)
+        tr = scenes.ground_plane() if plane else None
+        total = n + (2 if plane else 0)
+        for wi in (None, rng.permutation(total).astype(np.uint32)):
+            rank, n_nodes, depth = api.bvh_build_host(sp, tr, wi)
+            want, want_depth = O.leaf_order(sp, tr, wi)
+            assert np.array_equal(rank, want)
+            assert n_nodes == 2 * total - 1 and depth == want_depth
+            assert sorted(rank.tolist()) == list(range(total))
+    # coincident centroids → the "split the list in half" branch (bvh_impl.rs:277-290)
+    sp = scenes.synthetic_spheres(37, 5)
+    sp["center"] = (0, 0, -5)
+    assert np.array_equal(api.bvh_build_host(sp, None)[0], O.leaf_order(sp, None)[0])
+
+
+def test_host_bvh_errors(rt):
+    from rt_b200 import api, scenes
+
+    with pytest.raises(rt.RtError) as e:
+        api.bvh_build_host(None, None)
+    assert e.value.status == -2                                   # empty scene
+    sp = scenes.synthetic_spheres(4)
+    with pytest.raises(rt.RtError) as e:
+        api.bvh_build_host(sp, None, np.array([0, 1, 1, 2], dtype=np.uint32))
+    assert e.value.status == -1                                   # not a permutation
+    sp["center"][1] = (np.nan, 0, 0)
+    with pytest.raises(rt.RtError) as e:
+        api.bvh_build_host(sp, None)
+    assert e.value.status == -5
+
+
+def test_synthetic_scene_generator_is_pinned(rt):
+    from rt_b200 import scenes
+
+    g = scenes.SplitMix64(0)
+    assert g.next() == 0xE220A8397B1DCDAF                          # same stream as testbase.rs:321-327
+    a, b = scenes.synthetic_spheres(256), scenes.synthetic_spheres(256)
+    assert a.tobytes() == b.tobytes()
+    assert np.all(a["center"][:, 2] <= -4) and np.all(a["center"][:, 2] >= -20)
+    assert np.all((a["radius"] >= 0.175 - 1e-6) & (a["radius"] <= 0.35 + 1e-6))
+    assert 0 < (a["emission"] > 0).sum() < 40 and set(np.unique(a["roughness"] == 1.0)) == {False, True}
+    # first sphere of the default stream, pinned
+    s0 = scenes.synthetic_spheres(1)[0]
+    g = scenes.SplitMix64(0)
+    u = [g.u() for _ in range(4)]
+    assert s0["center"][0] == np.float32(-8 + 16 * u[0]) and s0["radius"] == np.float32(0.35 * 256 ** (1 / 3) * (0.5 + 0.5 * u[3]))
+    assert scenes.synthetic_spheres(8, 1).tobytes() != scenes.synthetic_spheres(8, 2).tobytes()
+    for name, c in scenes.CONFIGS.items():
+        sp, tr = scenes.config_scene(name)
+        assert len(sp) == c["n_spheres"] and len(tr) == (2 if c["plane"] else 0)
+
+
+def test_wire_roundtrip_and_shapes(rt):
+    from rt_b200 import scenes, wire
+
+    sp, tr = scenes.synthetic_spheres(5, 3), scenes.ground_plane()
+    wi = np.array([3, 0, 6, 1, 4, 2, 5], dtype=np.uint32)          # interleave spheres and triangles
+    meta = wire.RenderMeta(1080, 1920, 20, "123e4567-e89b-12d3-a456-426614174000")
+    text = wire.render_info_to_json(sp, tr, meta, 7, wi)
+    o = json.loads(text)
+    assert list(o.keys()) == ["world", "render_meta", "division_no"]
+    assert list(o["render_meta"].keys()) == ["height", "width", "divisions", "id"]
+    assert [list(x.keys())[0] for x in o["world"]] == ["Sphere", "Sphere", "Triangle", "Sphere", "Sphere", "Triangle", "Sphere"]
+    assert list(o["world"][0]["Sphere"].keys()) == ["radius", "center", "node_index", "p_albedo_at", "p_roughness_at", "p_emission_at"]
+    assert list(o["world"][2]["Triangle"].keys()) == ["a", "b", "c", "node_index", "p_albedo_at", "p_roughness_at", "p_emission_at"]
+    info = wire.parse_render_info(text)
+    assert info.division_no == 7 and info.render_meta == meta
+    assert info.world.spheres.tobytes() != b"" and len(info.world) == 7
+    # spheres come back in world order; map back through world_index and compare bit-for-bit
+    back = {int(p): info.world.spheres[i] for i, p in enumerate(info.world.world_index[:5])}
+    for i in range(5):
+        assert back[int(wi[i])].tobytes() == sp[i].tobytes()
+    backt = {int(p): info.world.triangles[i] for i, p in enumerate(info.world.world_index[5:])}
+    for j in range(2):
+        assert backt[int(wi[5 + j])].tobytes() == tr[j].tobytes()
+
+
+def test_image_slice_json(rt):
+    from rt_b200 import wire
+
+    sl = wire.ImageSlice(3, np.array([0, 1, 255, 17], dtype=np.uint8), "123e4567-e89b-12d3-a456-426614174000")
+    text = sl.to_json()
+    assert text == '{"division_no":3,"image":[0,1,255,17],"id":"123e4567-e89b-12d3-a456-426614174000"}'
+    back = wire.ImageSlice.from_json(text)
+    assert back.division_no == 3 and back.image.tolist() == [0, 1, 255, 17] and back.id == sl.id
+
+
+@pytest.mark.parametrize("body", [
+    b"not json", b"[]", b'{"world":[],"division_no":0}',
+    b'{"world":[{"Cube":{}}],"render_meta":{"height":1,"width":1,"divisions":1,"id":"123e4567-e89b-12d3-a456-426614174000"},"division_no":0}',
+    b'{"world":[{"Sphere":{"radius":1}}],"render_meta":{"height":1,"width":1,"divisions":1,"id":"123e4567-e89b-12d3-a456-426614174000"},"division_no":0}',
+    b'{"world":[],"render_meta":{"height":-1,"width":1,"divisions":1,"id":"123e4567-e89b-12d3-a456-426614174000"},"division_no":0}',
+    b'{"world":[],"render_meta":{"height":1,"width":1,"divisions":1,"id":"nope"},"division_no":0}',
+])
+def test_wire_rejects_malformed_bodies(rt, body):
+    from rt_b200 import wire
+
+    with pytest.raises(wire.WireError):
+        wire.parse_render_info(body)
+
+
+def test_tile_partition_is_exact_cover(rt):
+    from rt_b200 import multi
+
+    for (w, h) in [(64, 32), (101, 67), (1920, 1080)]:
+        tx, ty = multi.tile_grid(w, h)
+        for ranks in (1, 2, 3, 8):
+            owners = np.array([multi.tile_owner(t, ranks) for t in range(min(tx * ty, 5000))])
+            assert owners.min() >= 0 and owners.max() < ranks
+            # kernel's ticket map: rank r, ticket k → tile k*ranks + (r+k) % ranks
+            for r in range(ranks):
+                mine = multi.tiles_of_rank(w, h, r, ranks)
+                k = np.arange(len(mine) + 2)
+                g = k * ranks + (r + k) % ranks
+                assert np.array_equal(np.sort(g[g < tx * ty]), mine)
+            om = multi.owner_map(w, h, ranks)
+            assert om.shape == (h, w)
+            counts = np.bincount(om.reshape(-1), minlength=ranks)
+            assert counts.sum() == w * h and counts.min() > 0.8 * counts.max() - 64
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _gloo_worker(rank, world, port, w, h, q):
+    import torch
+    import torch.distributed as dist
+
+    from rt_b200 import multi
+
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    om = multi.owner_map(w, h, world)
+    # stand-in for the render kernel: each rank fills ITS tiles of a zeroed frame with a pixel-dependent value
+    yy, xx = np.mgrid[0:h, 0:w]
+    truth = ((yy * 31 + xx * 7) % 251 + 1).astype(np.uint8)
+    local = np.where(om == rank, truth, 0).astype(np.uint8)
+    frame = torch.from_numpy(np.repeat(local[..., None], 3, axis=2).copy().reshape(-1))
+    multi.assemble_reduce(frame, 0)
+    if rank == 0:
+        q.put(bool(np.array_equal(frame.numpy().reshape(h, w, 3)[..., 0], truth)))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gloo_world2_frame_assembly(rt):
+    """N>1 path on CPU: disjoint per-rank tiles + reduce(MAX) on rank 0 reproduce the whole frame."""
+    import torch.multiprocessing as mp
+
+    ctxm = mp.get_context("spawn")
+    q = ctxm.Queue()
+    port = _free_port()
+    procs = [ctxm.Process(target=_gloo_worker, args=(r, 2, port, 101, 67, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    ok = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert ok
