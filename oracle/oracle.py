@@ -90,6 +90,8 @@ def lib():
         L.orc_get_ray.argtypes = [C.POINTER(OrcParams), u32, u32, u64, vp]
         L.orc_nearest_hit.argtypes = [vp, u32, vp, u32, vp, vp, vp, i32, vp]
         L.orc_nearest_hit.restype = i32
+        L.orc_trace_pixel.argtypes = [vp, u32, vp, u32, vp, C.POINTER(OrcParams), u32, u32, i32, vp, u32]
+        L.orc_trace_pixel.restype = i32
         L.orc_f32_as_u8.argtypes = [C.c_float]
         L.orc_f32_as_u8.restype = C.c_uint8
         L.orc_hardware_threads.restype = i32
@@ -168,6 +170,17 @@ def nearest_hit(spheres, triangles, origin, direction, world_index=None, mode=0)
     if rc < 0:
         raise RuntimeError(f"orc_nearest_hit failed: {rc}")
     return (None if rc == 0 else out)
+
+
+def trace_pixel(spheres, triangles, params: OrcParams, x, y_global, world_index=None, mode=0, max_rays=4096):
+    """Every nearest-hit query of one pixel: array (n, 7) = origin, direction, winner world position or -1."""
+    spheres, triangles, wi = _scene_args(spheres, triangles, world_index)
+    log = np.zeros((max_rays, 7), dtype=np.float32)
+    n = lib().orc_trace_pixel(_ptr(spheres), len(spheres), _ptr(triangles), len(triangles), _ptr(wi), C.byref(params),
+                              x, y_global, mode, _ptr(log), max_rays)
+    if n < 0:
+        raise RuntimeError(f"orc_trace_pixel failed: {n}")
+    return log[:min(n, max_rays)].copy()
 
 
 def bvh_traverse_boxes(boxes, origin, direction):

@@ -646,6 +646,9 @@ struct Scene {
     int mode;  // 0 = reference BVH candidates, 1 = brute force over the whole world in order
 };
 
+// optional per-thread ray log (orc_trace_pixel): origin(3), direction(3), hit world position or -1
+thread_local std::vector<float>* g_ray_log = nullptr;
+
 Color ray_color(const Ray& ray, const Scene& sc, uint32_t depth, SmallRng& rng, Counters* ctr,
                 std::vector<uint32_t>& scratch) {
     if (depth == 0) {
@@ -661,6 +664,10 @@ Color ray_color(const Ray& ray, const Scene& sc, uint32_t depth, SmallRng& rng, 
         hit = intersect_list(sc.world, scratch.data(), scratch.size(), ray, &tb, ctr);
     } else {
         hit = intersect_list(sc.world, nullptr, sc.world.size(), ray, &tb, ctr);
+    }
+    if (g_ray_log) {
+        g_ray_log->insert(g_ray_log->end(), {ray.origin.x, ray.origin.y, ray.origin.z, ray.direction.x,
+                                             ray.direction.y, ray.direction.z, hit ? (float)tb.index : -1.0f});
     }
     if (hit) {
         if (tb.emission > 0.0f) {
@@ -996,6 +1003,38 @@ int orc_nearest_hit(const orc_sphere* sph, uint32_t ns, const orc_triangle* tri,
     out[6] = length(tb.point - r.origin);
     out[7] = (float)tb.index;
     return 1;
+}
+// Traces every sample of one pixel and logs each nearest-hit query: 7 floats per ray
+// (origin, direction, winner's world position or -1). Returns the number of rays (<= max_rays logged).
+int orc_trace_pixel(const orc_sphere* sph, uint32_t ns, const orc_triangle* tri, uint32_t nt,
+                    const uint32_t* world_index, const orc_params* params_in, uint32_t x, uint32_t y_global, int mode,
+                    float* log_out, uint32_t max_rays) {
+    orc_params p = *params_in;
+    fill_defaults(&p);
+    Scene sc;
+    sc.mode = mode;
+    if (!make_world(sph, ns, tri, nt, world_index, &sc.world)) return -1;
+    if (mode == 0) {
+        std::vector<AABB> boxes(sc.world.size());
+        for (size_t i = 0; i < boxes.size(); i++) boxes[i] = object_aabb(sc.world[i]);
+        if (!bvh_build(boxes, &sc.bvh)) return -2;
+    }
+    Camera cam = camera_new(v3(p.cam_origin[0], p.cam_origin[1], p.cam_origin[2]),
+                            (float)p.width / (float)p.height, p.aperture, p.focus_distance,
+                            p.field_of_view, p.focal_length, (float)p.height);
+    SmallRng rng = SmallRng::seed_from_u64(p.seed + ((uint64_t)y_global * p.width + x));
+    std::vector<float> log;
+    std::vector<uint32_t> scratch;
+    g_ray_log = &log;
+    for (uint32_t s = 0; s < p.spp; s++) {
+        Ray ray = camera_get_ray(cam, x, p.height - y_global - 1, rng);
+        ray_color(ray, sc, p.max_bounces + 1, rng, nullptr, scratch);
+    }
+    g_ray_log = nullptr;
+    uint32_t n = (uint32_t)(log.size() / 7);
+    for (uint32_t i = 0; i < n && i < max_rays; i++)
+        for (int k = 0; k < 7; k++) log_out[7 * i + k] = log[7 * i + k];
+    return (int)n;
 }
 uint8_t orc_f32_as_u8(float f) { return f32_as_u8(f); }
 int orc_hardware_threads() { return (int)std::thread::hardware_concurrency(); }

@@ -173,7 +173,7 @@ inline bool finite3(const float* v) { return std::isfinite(v[0]) && std::isfinit
 // World order + bounds + BVH, shared by rt_scene_create and rt_bvh_build_host.  Host only.
 static int build_world_bvh(const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles,
                            uint32_t n_triangles, const uint32_t* world_index, std::vector<PrimRef>* world_out,
-                           HostBVH* bvh, std::string* err) {
+                           HostBVH* bvh, std::string* err, std::vector<Box>* boxes_out = nullptr) {
     char buf[256];
     const uint32_t n = n_spheres + n_triangles;
     std::vector<PrimRef>& world = *world_out;
@@ -229,6 +229,7 @@ static int build_world_bvh(const rt_sphere* spheres, uint32_t n_spheres, const r
         *err = buf;
         return RT_ERR_UNSUPPORTED;
     }
+    if (boxes_out) boxes_out->swap(boxes);
     return RT_OK;
 }
 
@@ -267,10 +268,11 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         return set_err(ctx, RT_ERR_INVALID_ARG, "rt_scene_create: NULL primitive array");
     const uint32_t n = (uint32_t)n64;
     std::vector<PrimRef> world;
+    std::vector<Box> boxes;  // the reference's (unpadded) shape AABBs by world position
     HostBVH bvh;
     {
         std::string herr;
-        int hrc = build_world_bvh(spheres, n_spheres, triangles, n_triangles, world_index, &world, &bvh, &herr);
+        int hrc = build_world_bvh(spheres, n_spheres, triangles, n_triangles, world_index, &world, &bvh, &herr, &boxes);
         if (hrc) return set_err(ctx, hrc, "%s", herr.c_str());
     }
     // pids: spheres then triangles, each in DFS leaf order
@@ -293,7 +295,8 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     const size_t o_sph = take((size_t)n_spheres * 16), o_tri = take((size_t)n_triangles * 64);
     const size_t o_na = take((size_t)ni * 16), o_nb = take((size_t)ni * 16), o_nc = take((size_t)ni * 16);
     const size_t o_nd = take((size_t)ni * 8), o_mat = take((size_t)n * 16), o_em = take((size_t)n * 4);
-    const size_t o_rank = take((size_t)n * 4);
+    const size_t o_rank = take((size_t)n * 4), o_box = take((size_t)n * 32);
+    const size_t o_ca = take((size_t)ni * 16), o_cb = take((size_t)ni * 16), o_cc = take((size_t)ni * 16);
     std::vector<uint8_t> blob(off ? off : 256, 0);
     float* h_sph = (float*)(blob.data() + o_sph);
     float* h_tri = (float*)(blob.data() + o_tri);
@@ -305,9 +308,14 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     float* h_em = (float*)(blob.data() + o_em);
     uint32_t* h_rank = (uint32_t*)(blob.data() + o_rank);
 
+    float* h_box = (float*)(blob.data() + o_box);
     for (uint32_t w = 0; w < n; w++) {
         const uint32_t pid = pid_of_world[w];
         h_rank[pid] = rank_of_world[w];
+        for (int a = 0; a < 3; a++) {
+            h_box[8 * (size_t)pid + a] = boxes[w].min[a];
+            h_box[8 * (size_t)pid + 4 + a] = boxes[w].max[a];
+        }
         if (world[w].kind == 0) {
             const rt_sphere& s = spheres[world[w].idx];
             float* g = h_sph + 4 * (size_t)pid;
@@ -370,6 +378,27 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         c[0] = rl[2]; c[1] = rh[0]; c[2] = rh[1]; c[3] = rh[2];
         h_nd[2 * (size_t)i] = code_of(hn.left);
         h_nd[2 * (size_t)i + 1] = code_of(hn.right);
+        // centre / half-extent form (FILTER domain): t = (c - o)*inv -/+ h*|inv|.  h is padded for the
+        // rounding of the c- and h-terms (<= 2^-24 * (2|c| + h) per axis); the o-term is covered per ray.
+        auto centre_half = [](const Box& b, float c[3], float h[3]) {
+            double m = 0.0;
+            for (int a = 0; a < 3; a++) m = std::fmax(m, std::fmax(std::fabs((double)b.min[a]), std::fabs((double)b.max[a])));
+            for (int a = 0; a < 3; a++) {
+                double cc = 0.5 * ((double)b.min[a] + (double)b.max[a]);
+                double hh = 0.5 * ((double)b.max[a] - (double)b.min[a]);
+                c[a] = (float)cc;
+                h[a] = (float)(hh * (1.0 + 4e-6) + 2e-6 * m + 1e-30);
+            }
+        };
+        float lc[3], lhh[3], rc[3], rhh[3];
+        centre_half(hn.box_l, lc, lhh);
+        centre_half(hn.box_r, rc, rhh);
+        float* ca = (float*)(blob.data() + o_ca) + 4 * (size_t)i;
+        float* cb = (float*)(blob.data() + o_cb) + 4 * (size_t)i;
+        float* cc = (float*)(blob.data() + o_cc) + 4 * (size_t)i;
+        ca[0] = lc[0]; ca[1] = lc[1]; ca[2] = lc[2]; ca[3] = lhh[0];
+        cb[0] = lhh[1]; cb[1] = lhh[2]; cb[2] = rc[0]; cb[3] = rc[1];
+        cc[0] = rc[2]; cc[1] = rhh[0]; cc[2] = rhh[1]; cc[3] = rhh[2];
     }
 
     rt_scene* sc = new (std::nothrow) rt_scene();
@@ -395,9 +424,13 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     d.node_b = (const float4*)(sc->d_blob + o_nb);
     d.node_c = (const float4*)(sc->d_blob + o_nc);
     d.node_d = (const int2*)(sc->d_blob + o_nd);
+    d.cnode_a = (const float4*)(sc->d_blob + o_ca);
+    d.cnode_b = (const float4*)(sc->d_blob + o_cb);
+    d.cnode_c = (const float4*)(sc->d_blob + o_cc);
     d.mat = (const float4*)(sc->d_blob + o_mat);
     d.emis = (const float*)(sc->d_blob + o_em);
     d.rank = (const uint32_t*)(sc->d_blob + o_rank);
+    d.leaf_box = (const float4*)(sc->d_blob + o_box);
     d.ns = n_spheres;
     d.nt = n_triangles;
     d.ni = ni;

@@ -33,9 +33,13 @@ struct DevScene {
     const float4* node_b;  // [ni]    l.max.yz,  r.min.xy
     const float4* node_c;  // [ni]    r.min.z,   r.max.xyz
     const int2* node_d;    // [ni]    left code, right code
+    const float4* cnode_a; // [ni]    centre/half-extent form of the same boxes (scheduled kernel):
+    const float4* cnode_b; //         l.c.xyz, l.h.x | l.h.yz, r.c.xy | r.c.z, r.h.xyz
+    const float4* cnode_c;
     const float4* mat;     // [ns+nt] albedo rgb, roughness
     const float* emis;     // [ns+nt]
     const uint32_t* rank;  // [ns+nt] DFS leaf rank (exact-distance tie-break, shapes/mod.rs:177-182)
+    const float4* leaf_box;  // [(ns+nt)*2] the shape's own AABB exactly as the reference computes it (min | max)
     uint32_t ns, nt, ni;
     int root;              // child code of the root
 };
@@ -261,5 +265,31 @@ __device__ __forceinline__ bool triangle_root_exact(V3 o, V3 d, V3 a, V3 ab, V3 
 }
 
 __device__ __forceinline__ V3 ld3(const float4& v) { return mk(v.x, v.y, v.z); }
+
+// Ray::intersects_aabb (bvh/src/ray.rs:174-194) — EXACT, with Ray::new's cached 1/d and signs
+// (ray.rs:133-143) and the crate's own min/max (ray.rs:82-112: `if x < y {x} else {y}`).
+//
+// Why the GPU path needs it: the reference's BVH is NOT a conservative cull.  A primitive whose exact
+// hit lies a rounding error outside its own AABB (e.g. the border of an axis-aligned triangle) is
+// dropped by bvh.traverse() before intersect() ever sees it (main.rs:113-114).  Float subtraction and
+// multiplication are monotonic, and every ancestor's child box contains the shape's own box, so
+// "the shape's own AABB passes this test" implies every ancestor passes: one test per exact hit
+// reproduces the reference's candidate set (NaN slabs from 0*inf aside).
+__device__ __forceinline__ bool ref_intersects_aabb(V3 o, V3 d, V3 lo, V3 hi) {
+    const float ivx = x_div(1.0f, d.x), ivy = x_div(1.0f, d.y), ivz = x_div(1.0f, d.z);
+    const bool sx = d.x < 0.0f, sy = d.y < 0.0f, sz = d.z < 0.0f;
+    float ray_min = x_mul(x_sub(sx ? hi.x : lo.x, o.x), ivx);
+    float ray_max = x_mul(x_sub(sx ? lo.x : hi.x, o.x), ivx);
+    const float y_min = x_mul(x_sub(sy ? hi.y : lo.y, o.y), ivy);
+    const float y_max = x_mul(x_sub(sy ? lo.y : hi.y, o.y), ivy);
+    ray_min = (ray_min > y_min) ? ray_min : y_min;
+    ray_max = (ray_max < y_max) ? ray_max : y_max;
+    const float z_min = x_mul(x_sub(sz ? hi.z : lo.z, o.z), ivz);
+    const float z_max = x_mul(x_sub(sz ? lo.z : hi.z, o.z), ivz);
+    ray_min = (ray_min > z_min) ? ray_min : z_min;
+    ray_max = (ray_max < z_max) ? ray_max : z_max;
+    const float lo_t = (ray_min > 0.0f) ? ray_min : 0.0f;
+    return lo_t <= ray_max;
+}
 
 }  // namespace rtb

@@ -19,6 +19,8 @@
 #include "rt_host.h"
 
 #include <cstdio>
+#include <cstdlib>
+#include <cstring>
 
 namespace rtb {
 
@@ -49,8 +51,36 @@ struct SceneView {
 // Leaf tests.  `best` is updated iff the candidate wins the reference's min_by: smaller
 // length(p - o), ties to the smaller DFS leaf rank (shapes/mod.rs:174-182, bvh_impl.rs:373-398).
 // ---------------------------------------------------------------------------------------------
+// FILTER-domain shortcut for the reference's slab test on the shape's own box: when the hit point is inside
+// the box by a margin that dominates every rounding error of ray.rs:174-194 (2^-23 relative on each slab
+// product, plus the ~1e-6*t disagreement between a triangle's Moeller-Trumbore t and its flat box's slab t),
+// the reference test passes for certain.  Axes on which the box is flat (lo == hi: an axis-aligned triangle)
+// give the reference tmin == tmax bit for bit, so only the other axes need the margin.
+__device__ __forceinline__ bool robustly_inside(V3 p, float t, V3 lo, V3 hi) {
+    const float m0 = 4e-5f * fabsf(t);
+    bool ok = true;
+    {
+        const float m = fmaf(1e-6f, fabsf(p.x) + fabsf(lo.x) + fabsf(hi.x), m0);
+        ok = ok && ((lo.x == hi.x) || ((p.x - lo.x >= m) && (hi.x - p.x >= m)));
+    }
+    {
+        const float m = fmaf(1e-6f, fabsf(p.y) + fabsf(lo.y) + fabsf(hi.y), m0);
+        ok = ok && ((lo.y == hi.y) || ((p.y - lo.y >= m) && (hi.y - p.y >= m)));
+    }
+    {
+        const float m = fmaf(1e-6f, fabsf(p.z) + fabsf(lo.z) + fabsf(hi.z), m0);
+        ok = ok && ((lo.z == hi.z) || ((p.z - lo.z >= m) && (hi.z - p.z >= m)));
+    }
+    return ok;
+}
+
 __device__ __forceinline__ void consider(const DevScene& sc, V3 o, V3 d, float t, int pid, Hit& best) {
     V3 p = x_add(o, x_scale(d, t));   // Ray::at: origin + t*direction
+    // bvh.traverse() (main.rs:113): the shape is a candidate only if the reference's slab test lets it through
+    if (sc.ns + sc.nt > 1) {
+        const V3 blo = ld3(__ldg(&sc.leaf_box[2 * pid])), bhi = ld3(__ldg(&sc.leaf_box[2 * pid + 1]));
+        if (!robustly_inside(p, t, blo, bhi) && !ref_intersects_aabb(o, d, blo, bhi)) return;
+    }
     float dist = x_length(x_sub(p, o));
     bool take;
     if (best.pid < 0) {
@@ -101,6 +131,72 @@ __device__ __forceinline__ void test_triangle(const DevScene& sc, const float4* 
     float t;
     int stage;
     bool hit = triangle_root_exact(o, d, a, ab, ac, &t, &stage);
+    if (COUNT) {
+        if (stage >= 1) ctr.v[CTR_TRI_S1]++;
+        if (stage >= 2) ctr.v[CTR_TRI_S2]++;
+        if (stage >= 3) ctr.v[CTR_TRI_S3]++;
+        if (hit) ctr.v[CTR_TRI_HIT]++;
+    }
+    if (!hit) return;
+    consider(sc, o, d, t, pid, best);
+}
+
+// ---- the same tests split into a cheap FILTER stage and an EXACT stage (scheduled kernel) ----
+__device__ __forceinline__ bool sphere_filter(const float4 s, V3 o, V3 d) {
+    const float ocx = x_sub(o.x, s.x), ocy = x_sub(o.y, s.y), ocz = x_sub(o.z, s.z);
+    const float bh = fmaf(ocz, d.z, fmaf(ocy, d.y, ocx * d.x));
+    const float oc2 = fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx));
+    const float cf = oc2 - s.w;
+    const float disc = fmaf(bh, bh, -cf);
+    if (fmaf(oc2, 2e-5f, disc) < 0.0f) return false;
+    if (bh > 0.0f && cf > 1e-4f * oc2) return false;
+    return true;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void sphere_exact(const DevScene& sc, const float4 s, int pid, V3 o, V3 d, Hit& best,
+                                             Ctr& ctr) {
+    const V3 oc = mk(x_sub(o.x, s.x), x_sub(o.y, s.y), x_sub(o.z, s.z));
+    if (COUNT) ctr.v[CTR_SPH_EXACT]++;
+    float t;
+    if (!sphere_root_exact(d, oc, s.w, &t)) return;
+    if (COUNT) ctr.v[CTR_SPH_HIT]++;
+    consider(sc, o, d, t, pid, best);
+}
+
+// FMA Moeller-Trumbore with error-scaled margins: false only when the exact test (mesh.rs:109-161) must
+// reject, or when the hit would be farther than the current best by more than the tie margin.
+__device__ __forceinline__ bool triangle_filter(const float4* tri, int tidx, V3 o, V3 d, float cull) {
+    const V3 a = ld3(tri[4 * tidx + 0]), ab = ld3(tri[4 * tidx + 1]), ac = ld3(tri[4 * tidx + 2]);
+    const float ux = fmaf(d.y, ac.z, -ac.y * d.z), uy = fmaf(d.z, ac.x, -ac.z * d.x), uz = fmaf(d.x, ac.y, -ac.x * d.y);
+    const float det = fmaf(ab.z, uz, fmaf(ab.y, uy, ab.x * ux));
+    const float sdet = fabsf(ab.x * ux) + fabsf(ab.y * uy) + fabsf(ab.z * uz);
+    if (fabsf(det) < 1e-5f + 1e-4f * sdet) return true;  // near-parallel: let the exact test decide
+    const float inv = __frcp_rn(det), ainv = fabsf(inv);
+    const float aox = o.x - a.x, aoy = o.y - a.y, aoz = o.z - a.z;
+    const float mag = fabsf(aox) + fabsf(aoy) + fabsf(aoz);
+    const float mab = fabsf(ab.x) + fabsf(ab.y) + fabsf(ab.z), mac = fabsf(ac.x) + fabsf(ac.y) + fabsf(ac.z);
+    const float u = fmaf(aoz, uz, fmaf(aoy, uy, aox * ux)) * inv;
+    // 1e-4 = ~800 ulp on the products actually summed; the second term covers cancellation inside d x ac
+    const float eu = (1e-4f * (fabsf(aox * ux) + fabsf(aoy * uy) + fabsf(aoz * uz)) + 2e-6f * mag * mac) * ainv + 1e-5f;
+    if (u < -eu || u > 1.0f + eu) return false;
+    const float vx = fmaf(aoy, ab.z, -ab.y * aoz), vy = fmaf(aoz, ab.x, -ab.z * aox), vz = fmaf(aox, ab.y, -ab.x * aoy);
+    const float v = fmaf(d.z, vz, fmaf(d.y, vy, d.x * vx)) * inv;
+    const float ev = 1e-4f * mag * mab * ainv + 1e-5f;  // |d| = 1
+    if (v < -ev || u + v > 1.0f + eu + ev) return false;
+    const float t = fmaf(ac.z, vz, fmaf(ac.y, vy, ac.x * vx)) * inv;
+    const float et = 1e-4f * mag * mab * mac * ainv + 1e-6f;
+    if (t < 0.0009f - et || t > cull + et) return false;  // exact needs t in [T_MIN, T_MAX) and a chance to win
+    return true;
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void triangle_exact(const DevScene& sc, const float4* tri, int tidx, int pid, V3 o, V3 d,
+                                               Hit& best, Ctr& ctr) {
+    const V3 a = ld3(tri[4 * tidx + 0]), ab = ld3(tri[4 * tidx + 1]), ac = ld3(tri[4 * tidx + 2]);
+    float t;
+    int stage;
+    const bool hit = triangle_root_exact(o, d, a, ab, ac, &t, &stage);
     if (COUNT) {
         if (stage >= 1) ctr.v[CTR_TRI_S1]++;
         if (stage >= 2) ctr.v[CTR_TRI_S2]++;
@@ -395,6 +491,10 @@ __global__ void __launch_bounds__(THREADS) render_kernel(const DevScene sc, cons
     }
 }
 
+}  // namespace rtb
+#include "rt_kernel_sched.cuh"
+namespace rtb {
+
 // ---------------------------------------------------------------------------------------------
 // FFMA-chain micro-benchmark for the FP32 roofline denominator
 // ---------------------------------------------------------------------------------------------
@@ -423,8 +523,30 @@ template <int ISECT, bool SMEM>
 static KernelFn pick_count(bool count) {
     return count ? (KernelFn)render_kernel<ISECT, SMEM, true> : (KernelFn)render_kernel<ISECT, SMEM, false>;
 }
+// RT_B200_BVH_KERNEL=simple selects the first (unscheduled) BVH megakernel, kept for A/B measurements
+static bool use_sched_kernel() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = std::getenv("RT_B200_BVH_KERNEL");
+        v = (e && std::strcmp(e, "simple") == 0) ? 0 : 1;
+    }
+    return v == 1;
+}
 static KernelFn pick_kernel(int isect, bool smem, bool count) {
     if (isect == RT_INTERSECT_BRUTE) return smem ? pick_count<RT_INTERSECT_BRUTE, true>(count) : pick_count<RT_INTERSECT_BRUTE, false>(count);
+    if (use_sched_kernel()) {
+        static int minb = -1;  // RT_B200_SCHED_MINB=3 trades registers (<= 80) for 24 resident warps per SM
+        if (minb < 0) {
+            const char* e = std::getenv("RT_B200_SCHED_MINB");
+            minb = (e && std::atoi(e) == 3) ? 3 : 2;
+        }
+        if (minb == 3) {
+            if (smem) return count ? (KernelFn)render_kernel_sched<true, true, 3> : (KernelFn)render_kernel_sched<true, false, 3>;
+            return count ? (KernelFn)render_kernel_sched<false, true, 3> : (KernelFn)render_kernel_sched<false, false, 3>;
+        }
+        if (smem) return count ? (KernelFn)render_kernel_sched<true, true, 2> : (KernelFn)render_kernel_sched<true, false, 2>;
+        return count ? (KernelFn)render_kernel_sched<false, true, 2> : (KernelFn)render_kernel_sched<false, false, 2>;
+    }
     return smem ? pick_count<RT_INTERSECT_BVH, true>(count) : pick_count<RT_INTERSECT_BVH, false>(count);
 }
 
