@@ -6,6 +6,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -297,6 +298,8 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     const size_t o_nd = take((size_t)ni * 8), o_mat = take((size_t)n * 16), o_em = take((size_t)n * 4);
     const size_t o_rank = take((size_t)n * 4), o_box = take((size_t)n * 32);
     const size_t o_ca = take((size_t)ni * 16), o_cb = take((size_t)ni * 16), o_cc = take((size_t)ni * 16);
+    const size_t o_la = take((size_t)ni * 16), o_lb = take((size_t)ni * 16), o_lc = take((size_t)ni * 16);
+    const size_t o_ld = take((size_t)ni * 8);
     std::vector<uint8_t> blob(off ? off : 256, 0);
     float* h_sph = (float*)(blob.data() + o_sph);
     float* h_tri = (float*)(blob.data() + o_tri);
@@ -401,6 +404,73 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         cc[0] = rc[2]; cc[1] = rhh[0]; cc[2] = rhh[1]; cc[3] = rhh[2];
     }
 
+    // ---- collapsed tree for the lanes kernel: subtrees of <= L same-kind primitives become one leaf ----
+    uint32_t lni = 0;
+    int32_t lroot = 0;
+    {
+        int L = 1;  // RT_B200_LEAF: primitives per leaf (1..32). Measured on C3: 1 → 51.8 ms, 4 → 54.6, 16 → 62.7 (profiles/)
+        if (const char* e = std::getenv("RT_B200_LEAF")) L = std::atoi(e);
+        if (L < 1) L = 1;
+        if (L > 32) L = 32;
+        struct Sub { uint32_t n_s, n_t, first_s, first_t; };
+        auto leaf_sub = [&](int32_t code) {
+            const uint32_t w = (uint32_t)~code, pid = pid_of_world[w];
+            return world[w].kind == 0 ? Sub{1, 0, pid, 0} : Sub{0, 1, 0, pid};
+        };
+        std::vector<Sub> sub(ni);
+        auto sub_of = [&](int32_t code) { return code >= 0 ? sub[(size_t)code] : leaf_sub(code); };
+        for (uint32_t i = ni; i-- > 0;) {  // pre-order: children have larger indices than their parent
+            const Sub a = sub_of(bvh.inner[i].left), b = sub_of(bvh.inner[i].right);
+            sub[i] = Sub{a.n_s + b.n_s, a.n_t + b.n_t, a.n_s ? a.first_s : b.first_s, a.n_t ? a.first_t : b.first_t};
+        }
+        float* la = (float*)(blob.data() + o_la);
+        float* lb = (float*)(blob.data() + o_lb);
+        float* lc = (float*)(blob.data() + o_lc);
+        int32_t* ld = (int32_t*)(blob.data() + o_ld);
+        const float* ca = (const float*)(blob.data() + o_ca);
+        const float* cb = (const float*)(blob.data() + o_cb);
+        const float* cc = (const float*)(blob.data() + o_cc);
+        auto leaf_code = [](uint32_t first, uint32_t count) { return ~(int32_t)((first << 5) | (count - 1)); };
+        // iterative emit (explicit stack): (original code, slot to patch)
+        struct Item { int32_t code; uint32_t parent; int side; };
+        std::vector<Item> todo;
+        auto classify = [&](int32_t code, bool* is_leaf) -> int32_t {
+            const Sub sb = sub_of(code);
+            const uint32_t tot = sb.n_s + sb.n_t;
+            if (code < 0 || (tot <= (uint32_t)L && (sb.n_s == 0 || sb.n_t == 0))) {
+                *is_leaf = true;
+                return leaf_code(sb.n_s ? sb.first_s : sb.first_t, tot);
+            }
+            *is_leaf = false;
+            return 0;
+        };
+        bool root_leaf;
+        lroot = classify(bvh.root, &root_leaf);
+        if (!root_leaf) {
+            todo.push_back(Item{bvh.root, 0, -1});
+            while (!todo.empty()) {
+                const Item it = todo.back();
+                todo.pop_back();
+                const uint32_t me = lni++;
+                if (it.side < 0) lroot = (int32_t)me;
+                else ld[2 * (size_t)it.parent + it.side] = (int32_t)me;
+                const size_t src = (size_t)it.code;
+                for (int k = 0; k < 4; k++) {
+                    la[4 * (size_t)me + k] = ca[4 * src + k];
+                    lb[4 * (size_t)me + k] = cb[4 * src + k];
+                    lc[4 * (size_t)me + k] = cc[4 * src + k];
+                }
+                const int32_t kids[2] = {bvh.inner[src].left, bvh.inner[src].right};
+                for (int side = 1; side >= 0; side--) {  // push right first so the left subtree is numbered first
+                    bool is_leaf;
+                    const int32_t c = classify(kids[side], &is_leaf);
+                    if (is_leaf) ld[2 * (size_t)me + side] = c;
+                    else todo.push_back(Item{kids[side], me, side});
+                }
+            }
+        }
+    }
+
     rt_scene* sc = new (std::nothrow) rt_scene();
     if (!sc) return set_err(ctx, RT_ERR_INVALID_ARG, "out of host memory");
     sc->n = n;
@@ -427,6 +497,12 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     d.cnode_a = (const float4*)(sc->d_blob + o_ca);
     d.cnode_b = (const float4*)(sc->d_blob + o_cb);
     d.cnode_c = (const float4*)(sc->d_blob + o_cc);
+    d.lnode_a = (const float4*)(sc->d_blob + o_la);
+    d.lnode_b = (const float4*)(sc->d_blob + o_lb);
+    d.lnode_c = (const float4*)(sc->d_blob + o_lc);
+    d.lnode_d = (const int2*)(sc->d_blob + o_ld);
+    d.lni = lni;
+    d.lroot = lroot;
     d.mat = (const float4*)(sc->d_blob + o_mat);
     d.emis = (const float*)(sc->d_blob + o_em);
     d.rank = (const uint32_t*)(sc->d_blob + o_rank);

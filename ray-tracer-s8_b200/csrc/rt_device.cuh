@@ -36,6 +36,14 @@ struct DevScene {
     const float4* cnode_a; // [ni]    centre/half-extent form of the same boxes (scheduled kernel):
     const float4* cnode_b; //         l.c.xyz, l.h.x | l.h.yz, r.c.xy | r.c.z, r.h.xyz
     const float4* cnode_c;
+    // the same tree with every subtree of <= L same-kind primitives collapsed into one leaf (lanes kernel):
+    // pids are in DFS order, so a subtree is a contiguous pid range; leaf code = ~((first_pid << 5) | (count-1))
+    const float4* lnode_a;
+    const float4* lnode_b;
+    const float4* lnode_c;
+    const int2* lnode_d;
+    uint32_t lni;          // inner nodes of the collapsed tree
+    int lroot;             // its root code
     const float4* mat;     // [ns+nt] albedo rgb, roughness
     const float* emis;     // [ns+nt]
     const uint32_t* rank;  // [ns+nt] DFS leaf rank (exact-distance tie-break, shapes/mod.rs:177-182)
@@ -62,6 +70,9 @@ struct DevParams {
     uint32_t tiles_x, tiles_y;
     unsigned int* tile_counter;  // zeroed before launch
     unsigned long long* counters;  // NUM_COUNTERS
+    // scheduled kernels: pool weights (NODE, LEAF, HIT, PRIM) and the NODE phase's stay-in-loop share num/den
+    int sched_w[4];
+    int sched_node_num, sched_node_den;
 };
 
 enum CounterSlot {

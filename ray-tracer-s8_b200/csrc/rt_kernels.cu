@@ -56,8 +56,8 @@ struct SceneView {
 // product, plus the ~1e-6*t disagreement between a triangle's Moeller-Trumbore t and its flat box's slab t),
 // the reference test passes for certain.  Axes on which the box is flat (lo == hi: an axis-aligned triangle)
 // give the reference tmin == tmax bit for bit, so only the other axes need the margin.
-__device__ __forceinline__ bool robustly_inside(V3 p, float t, V3 lo, V3 hi) {
-    const float m0 = 4e-5f * fabsf(t);
+__device__ __forceinline__ bool robustly_inside(V3 p, float t, V3 lo, V3 hi, float extra = 0.0f) {
+    const float m0 = fmaf(4e-5f, fabsf(t), extra);
     bool ok = true;
     {
         const float m = fmaf(1e-6f, fabsf(p.x) + fabsf(lo.x) + fabsf(hi.x), m0);
@@ -205,6 +205,102 @@ __device__ __forceinline__ void triangle_exact(const DevScene& sc, const float4*
     }
     if (!hit) return;
     consider(sc, o, d, t, pid, best);
+}
+
+// ---- FILTER-domain distance bounds (deferred-exact traversal) ------------------------------------------
+// Each returns CL_MISS when the reference's exact test must reject the primitive, else an interval [lo, hi]
+// that contains the reference's length(point - origin) IF the exact test accepts it.  CL_SURE additionally
+// guarantees that the exact test accepts (roots well conditioned, t-range and the own-box slab test passed
+// by margins that dominate every rounding error), so `hi` may be used to cull farther candidates.
+enum { CL_MISS = 0, CL_MAYBE = 1, CL_SURE = 2 };
+
+__device__ __forceinline__ int sphere_bounds(const float4 s, V3 o, V3 d, float eo, bool check_box, float* lo,
+                                             float* hi) {
+    const float ocx = x_sub(o.x, s.x), ocy = x_sub(o.y, s.y), ocz = x_sub(o.z, s.z);
+    const float bh = fmaf(ocz, d.z, fmaf(ocy, d.y, ocx * d.x));
+    const float oc2 = fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx));
+    const float cf = oc2 - s.w;
+    const float disc = fmaf(bh, bh, -cf);
+    const float e_d = fmaf(oc2 + s.w, 2e-5f, 1e-30f);  // >> every rounding of the reference's b*b - 4*c (~300 ulp)
+    if (disc < -e_d) return CL_MISS;
+    if (bh > 0.0f && cf > 1e-4f * oc2) return CL_MISS;   // both roots behind the origin
+    const float m1 = fabsf(ocx) + fabsf(ocy) + fabsf(ocz);
+    *hi = 0.0f;
+    if (disc < 64.0f * e_d) {  // grazing: roots ill-conditioned, let the exact arithmetic decide
+        const float sqm = sqrtf(fmaxf(disc, 0.0f) + e_d);
+        const float eb = 4e-6f * m1 + eo;
+        if (-bh + sqm + eb < T_MIN) return CL_MISS;
+        *lo = -bh - sqm - eb;
+        return CL_MAYBE;
+    }
+    const float sq = sqrtf(disc);
+    const float e_t = __fdividef(0.51f * e_d, sq) + 2e-6f * (m1 + sq);
+    const float t0 = -bh - sq, t1 = -bh + sq;
+    float t;
+    if (t0 > T_MIN + e_t) {
+        t = t0;
+    } else if (t0 < T_MIN - e_t) {
+        if (t1 < T_MIN - e_t) return CL_MISS;
+        if (t1 <= T_MIN + e_t) {
+            *lo = t1 - e_t - eo;
+            return CL_MAYBE;
+        }
+        t = t1;
+    } else {
+        *lo = t0 - e_t - eo;
+        return CL_MAYBE;
+    }
+    const float e = e_t + eo + 1e-6f * t;
+    *lo = t - e;
+    *hi = t + e;
+    if (t > 999.0f) return t > 1001.0f ? CL_MISS : CL_MAYBE;
+    if (check_box) {  // the reference's slab test on the sphere's own box: certain when the point is well inside
+        const float r = sqrtf(s.w);
+        const V3 p = mk(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
+        if (!robustly_inside(p, t, mk(s.x - r, s.y - r, s.z - r), mk(s.x + r, s.y + r, s.z + r), e)) return CL_MAYBE;
+    }
+    return CL_SURE;
+}
+
+__device__ __forceinline__ int triangle_bounds(const float4* tri, int tidx, V3 o, V3 d, float eo, bool check_box,
+                                               float* lo, float* hi) {
+    const V3 a = ld3(tri[4 * tidx + 0]), ab = ld3(tri[4 * tidx + 1]), ac = ld3(tri[4 * tidx + 2]);
+    const float ux = fmaf(d.y, ac.z, -ac.y * d.z), uy = fmaf(d.z, ac.x, -ac.z * d.x), uz = fmaf(d.x, ac.y, -ac.x * d.y);
+    const float det = fmaf(ab.z, uz, fmaf(ab.y, uy, ab.x * ux));
+    const float sdet = fabsf(ab.x * ux) + fabsf(ab.y * uy) + fabsf(ab.z * uz);
+    *hi = 0.0f;
+    if (fabsf(det) < 1e-5f + 1e-4f * sdet) {  // near-parallel: only the exact test can tell
+        *lo = 0.0f;
+        return CL_MAYBE;
+    }
+    const float inv = __frcp_rn(det), ainv = fabsf(inv);
+    const float aox = o.x - a.x, aoy = o.y - a.y, aoz = o.z - a.z;
+    const float mag = fabsf(aox) + fabsf(aoy) + fabsf(aoz);
+    const float mab = fabsf(ab.x) + fabsf(ab.y) + fabsf(ab.z), mac = fabsf(ac.x) + fabsf(ac.y) + fabsf(ac.z);
+    const float u = fmaf(aoz, uz, fmaf(aoy, uy, aox * ux)) * inv;
+    // 1e-4 = ~800 ulp on the products actually summed; the second term covers cancellation inside d x ac
+    const float eu = (1e-4f * (fabsf(aox * ux) + fabsf(aoy * uy) + fabsf(aoz * uz)) + 2e-6f * mag * mac) * ainv + 1e-5f;
+    if (u < -eu || u > 1.0f + eu) return CL_MISS;
+    const float vx = fmaf(aoy, ab.z, -ab.y * aoz), vy = fmaf(aoz, ab.x, -ab.z * aox), vz = fmaf(aox, ab.y, -ab.x * aoy);
+    const float v = fmaf(d.z, vz, fmaf(d.y, vy, d.x * vx)) * inv;
+    const float ev = 1e-4f * mag * mab * ainv + 1e-5f;  // |d| = 1
+    if (v < -ev || u + v > 1.0f + eu + ev) return CL_MISS;
+    const float t = fmaf(ac.z, vz, fmaf(ac.y, vy, ac.x * vx)) * inv;
+    const float et = 1e-4f * mag * mab * mac * ainv + 1e-6f;
+    if (t < T_MIN - et || t > 1001.0f + et) return CL_MISS;  // EPSILON = 1e-5 < T_MIN
+    const float e = et + eo + 1e-6f * fabsf(t);
+    *lo = t - e;
+    *hi = t + e;
+    const bool inside = (u >= eu) && (u <= 1.0f - eu) && (v >= ev) && (u + v <= 1.0f - eu - ev);
+    if (!inside || t <= T_MIN + et || t > 999.0f) return CL_MAYBE;
+    if (check_box) {
+        const V3 b = mk(a.x + ab.x, a.y + ab.y, a.z + ab.z), c = mk(a.x + ac.x, a.y + ac.y, a.z + ac.z);
+        const V3 blo = mk(fminf(a.x, fminf(b.x, c.x)), fminf(a.y, fminf(b.y, c.y)), fminf(a.z, fminf(b.z, c.z)));
+        const V3 bhi = mk(fmaxf(a.x, fmaxf(b.x, c.x)), fmaxf(a.y, fmaxf(b.y, c.y)), fmaxf(a.z, fmaxf(b.z, c.z)));
+        const V3 p = mk(fmaf(t, d.x, o.x), fmaf(t, d.y, o.y), fmaf(t, d.z, o.z));
+        if (!robustly_inside(p, t, blo, bhi, e)) return CL_MAYBE;
+    }
+    return CL_SURE;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -491,8 +587,266 @@ __global__ void __launch_bounds__(THREADS) render_kernel(const DevScene sc, cons
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// K2 traversal, second form: centre/half-extent slab test (9 FFMA + 4 FMNMX per box instead of 6 FFMA +
+// 10 FMNMX: the first form saturated the ALU pipe at 75 % with the FMA pipe at 23 %), FMA pre-filter in
+// front of the exact triangle test.  Same while-while structure, same results.
+// ---------------------------------------------------------------------------------------------
+template <bool COUNT>
+__device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
+    best.pid = -1;
+    best.dist = 0.0f;
+    // FILTER-domain ray constants; |1/d| is clamped so 0*inf never produces NaN slabs
+    const float BIG = 1e30f;
+    float ix = fminf(fmaxf(__frcp_rn(d.x), -BIG), BIG);
+    float iy = fminf(fmaxf(__frcp_rn(d.y), -BIG), BIG);
+    float iz = fminf(fmaxf(__frcp_rn(d.z), -BIG), BIG);
+    if (!(fabsf(d.x) > 0.0f)) ix = BIG;
+    if (!(fabsf(d.y) > 0.0f)) iy = BIG;
+    if (!(fabsf(d.z) > 0.0f)) iz = BIG;
+    const float ax = fabsf(ix), ay = fabsf(iy), az = fabsf(iz);
+    const float qx = -o.x * ix, qy = -o.y * iy, qz = -o.z * iz;
+    // rounding of the o-term: <= 3 * 2^-24 * |o*inv| per axis, in t (the c- and h-terms are padded on the host)
+    const float slack = 4.8e-7f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 1e-30f;
+    float cull = 1001.0f;  // a hit has t < T_MAX and length(p-o) ~ t
+    int stack[MAX_STACK];
+    int sp = 0;
+    int cur = sc.lroot;
+    const int ns = (int)sc.ns;
+    for (;;) {
+        while (cur >= 0) {
+            const float4 a = sv.na[cur], b = sv.nb[cur], c = sv.nc[cur];
+            const int2 ch = sv.nd[cur];
+            // left box: c = (a.x,a.y,a.z) h = (a.w,b.x,b.y); right: c = (b.z,b.w,c.x) h = (c.y,c.z,c.w)
+            const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
+            const float rcx = fmaf(b.z, ix, qx), rcy = fmaf(b.w, iy, qy), rcz = fmaf(c.x, iz, qz);
+            const float tl = fmaxf(fmaxf(fmaf(-a.w, ax, lcx), fmaf(-b.x, ay, lcy)), fmaxf(fmaf(-b.y, az, lcz), 0.0f));
+            const float fl = fminf(fminf(fmaf(a.w, ax, lcx), fmaf(b.x, ay, lcy)), fminf(fmaf(b.y, az, lcz), cull));
+            const float tr = fmaxf(fmaxf(fmaf(-c.y, ax, rcx), fmaf(-c.z, ay, rcy)), fmaxf(fmaf(-c.w, az, rcz), 0.0f));
+            const float fr = fminf(fminf(fmaf(c.y, ax, rcx), fmaf(c.z, ay, rcy)), fminf(fmaf(c.w, az, rcz), cull));
+            const bool hl = tl <= fl + slack;
+            const bool hr = tr <= fr + slack;
+            if (COUNT) ctr.v[CTR_SLAB] += 2;
+            if (hl && hr) {
+                const bool swap = tr < tl;
+                stack[sp++] = swap ? ch.x : ch.y;
+                cur = swap ? ch.y : ch.x;
+            } else if (hl) {
+                cur = ch.x;
+            } else if (hr) {
+                cur = ch.y;
+            } else {
+                if (sp == 0) return;
+                cur = stack[--sp];
+            }
+        }
+        // leaf = contiguous pid range of one kind: code = ~((first << 5) | (count - 1))
+        const int first = (~cur) >> 5, count = ((~cur) & 31) + 1;
+        if (first < ns) {
+            for (int i = 0; i < count; i++) test_sphere<COUNT>(sc, sv.sph[first + i], first + i, o, d, best, ctr);
+        } else {
+            for (int i = 0; i < count; i++) {
+                const int pid = first + i;
+                if (COUNT) ctr.v[CTR_TRI_TEST]++;
+                if (triangle_filter(sv.tri, pid - ns, o, d, cull)) triangle_exact<COUNT>(sc, sv.tri, pid - ns, pid, o, d, best, ctr);
+            }
+        }
+        if (best.pid >= 0) cull = fmaf(best.dist, 1.00001f, 1e-6f);
+        if (sp == 0) return;
+        cur = stack[--sp];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// The megakernel, second form: lanes are independent workers.  A lane that finishes its pixel takes the
+// next pixel of the warp's current 8x4 tile (the warp pulls tiles from the global ticket counter) instead of
+// idling until the slowest pixel of the tile is done; every trip of the loop is one nearest-hit query.
+// ---------------------------------------------------------------------------------------------
+template <int ISECT, bool SMEM, bool COUNT>
+__global__ void __launch_bounds__(THREADS, 3) render_kernel_lanes(const DevScene sc, const DevCamera cam,
+                                                                const DevParams pr) {
+    extern __shared__ float4 smem_dyn[];
+    SceneView sv;
+    if (SMEM) {
+        float4* p = smem_dyn;
+        float4* s_sph = p;  p += sc.ns;
+        float4* s_tri = p;  p += 4 * sc.nt;
+        float4* s_na = p;   p += sc.ni;
+        float4* s_nb = p;   p += sc.ni;
+        float4* s_nc = p;   p += sc.ni;
+        int2* s_nd = reinterpret_cast<int2*>(p);
+        for (uint32_t i = threadIdx.x; i < sc.ns; i += THREADS) s_sph[i] = __ldg(&sc.sph[i]);
+        for (uint32_t i = threadIdx.x; i < 4 * sc.nt; i += THREADS) s_tri[i] = __ldg(&sc.tri[i]);
+        if (ISECT == RT_INTERSECT_BVH) {
+            for (uint32_t i = threadIdx.x; i < sc.lni; i += THREADS) {
+                s_na[i] = __ldg(&sc.lnode_a[i]);
+                s_nb[i] = __ldg(&sc.lnode_b[i]);
+                s_nc[i] = __ldg(&sc.lnode_c[i]);
+                s_nd[i] = __ldg(&sc.lnode_d[i]);
+            }
+        }
+        __syncthreads();
+        sv.sph = s_sph; sv.tri = s_tri; sv.na = s_na; sv.nb = s_nb; sv.nc = s_nc; sv.nd = s_nd;
+    } else {
+        sv.sph = sc.sph; sv.tri = sc.tri; sv.na = sc.lnode_a; sv.nb = sc.lnode_b; sv.nc = sc.lnode_c; sv.nd = sc.lnode_d;
+    }
+
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const uint32_t total_tiles = pr.tiles_x * pr.tiles_y;
+    const float spp_f = (float)pr.spp;
+
+    Ctr ctr;
+#pragma unroll
+    for (int i = 0; i < NUM_COUNTERS; i++) ctr.v[i] = 0;
+    unsigned long long rays = 0;
+
+    bool have_px = false, finished = false;
+    uint32_t px = 0, py = 0, s = 0, left = 0, np = 0;
+    float sr = 0.0f, sg = 0.0f, sb = 0.0f;
+    Rng rng;
+    rng.s0 = rng.s1 = rng.s2 = rng.s3 = 0;
+    V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
+    uint32_t path[MAX_PATH];  // pids of the non-terminal hits of the current sample
+
+    uint32_t tile_next = TILE_W * TILE_H;  // warp-uniform tile cursor (exhausted)
+    uint32_t tile_x0 = 0, tile_y0 = 0;
+    bool tiles_left = true;
+
+    for (;;) {
+        // ---- hand out pixels: warp-cooperative, tile by tile ----
+        unsigned want = __ballot_sync(FULL, !have_px && !finished);
+        while (want) {
+            if (tile_next >= (uint32_t)(TILE_W * TILE_H)) {
+                unsigned int k = 0;
+                if (tiles_left) {
+                    if (lane == 0) k = atomicAdd(pr.tile_counter, 1u);
+                    k = __shfl_sync(FULL, k, 0);
+                }
+                const uint64_t g = (uint64_t)k * pr.tile_ranks + (pr.tile_rank + k) % pr.tile_ranks;
+                if (!tiles_left || g >= total_tiles) {
+                    tiles_left = false;
+                    if (!have_px) finished = true;
+                    break;
+                }
+                tile_x0 = (uint32_t)(g % pr.tiles_x) * TILE_W;
+                tile_y0 = pr.row0 + (uint32_t)(g / pr.tiles_x) * TILE_H;
+                tile_next = 0;
+            }
+            const uint32_t avail = TILE_W * TILE_H - tile_next;
+            const uint32_t my = __popc(want & lt_mask);
+            if (!have_px && !finished && my < avail) {
+                const uint32_t j = tile_next + my;
+                const uint32_t x = tile_x0 + (j & (TILE_W - 1)), y = tile_y0 + (j / TILE_W);
+                if (x < pr.width && y < pr.row1) {  // tiles on the right/bottom edge are partial
+                    px = x; py = y;
+                    have_px = true;
+                    rng.seed_from_u64(pr.seed + ((uint64_t)y * pr.width + x));
+                    sr = sg = sb = 0.0f;
+                    s = 0;
+                    left = 0;
+                }
+            }
+            tile_next += min((uint32_t)__popc(want), avail);
+            want = __ballot_sync(FULL, !have_px && !finished);
+        }
+        if (__ballot_sync(FULL, have_px) == 0) break;
+
+        if (have_px) {
+            if (left == 0) {  // start sample s
+                primary_ray(cam, px, pr.height - py - 1, rng, &o, &d);  // y_cam = h - y - 1 (main.rs:71)
+                left = pr.depth;
+                np = 0;
+            }
+            // ---- one nearest-hit query (ray_color with depth > 0) ----
+            rays++;
+            if (COUNT) {
+                ctr.v[CTR_ACTIVE_LANES]++;
+                unsigned am = __activemask();
+                if (lane == (__ffs(am) - 1)) ctr.v[CTR_TOTAL_LANES] += 32;
+            }
+            Hit h;
+            if (ISECT == RT_INTERSECT_BRUTE) trace_brute<COUNT>(sc, sv, o, d, h, ctr);
+            else trace_bvh_ch<COUNT>(sc, sv, o, d, h, ctr);
+
+            bool done;
+            float Lr, Lg, Lb;
+            if (h.pid >= 0) {
+                const float e = __ldg(&sc.emis[h.pid]);
+                const float4 m = __ldg(&sc.mat[h.pid]);
+                if (e > 0.0f) {  // emission * albedo (main.rs:116-117)
+                    Lr = x_mul(m.x, e); Lg = x_mul(m.y, e); Lb = x_mul(m.z, e);
+                    done = true;
+                    if (COUNT) ctr.v[CTR_EMISSIVE]++;
+                } else {
+                    V3 n;
+                    if (COUNT) ctr.v[h.pid < (int)sc.ns ? CTR_SHADE_SPH : CTR_SHADE_TRI]++;
+                    if (h.pid < (int)sc.ns) {
+                        n = x_normalize_or_zero(x_sub(h.p, ld3(sv.sph[h.pid])));  // sphere.rs:49-51
+                    } else {
+                        n = ld3(sv.tri[4 * (h.pid - (int)sc.ns) + 3]);  // mesh.rs:163-165 (host, same ops)
+                    }
+                    V3 diffuse = x_add(unit_sphere(rng), n);
+                    float kk = x_mul(2.0f, x_dot(d, n));
+                    V3 glossy = x_sub(d, x_scale(n, kk));
+                    V3 scat = x_add(diffuse, x_scale(x_sub(glossy, diffuse), m.w));
+                    V3 nd;
+                    if (!x_try_normalize(scat, &nd)) nd = n;
+                    o = h.p;
+                    d = x_normalize_div(nd);  // Ray::new
+                    path[np++] = (uint32_t)h.pid;
+                    left--;
+                    done = (left == 0);       // next call has depth == 0 → BLACK, no query
+                    Lr = Lg = Lb = 0.0f;
+                }
+            } else {  // sky (main.rs:135-144)
+                if (COUNT) ctr.v[CTR_SKY]++;
+                float rcp = x_div(1.0f, x_length(d));
+                float ny = (isfinite(rcp) && rcp > 0.0f) ? x_mul(d.y, rcp) : 0.0f;
+                float t = x_add(x_mul(ny, 0.5f), 1.0f);
+                float k1 = x_sub(1.0f, t);
+                float w = x_mul(1.0f, t);
+                Lr = x_add(w, x_mul(0.3f, k1));
+                Lg = Lr;
+                Lb = x_add(w, x_mul(0.8f, k1));
+                done = true;
+            }
+            if (done) {
+                // fold albedo ⊙ (albedo ⊙ (... ⊙ L)) innermost first, like the recursion unwinding
+                while (np > 0) {
+                    const float4 m = __ldg(&sc.mat[path[--np]]);
+                    Lr = x_mul(m.x, Lr); Lg = x_mul(m.y, Lg); Lb = x_mul(m.z, Lb);
+                }
+                sr = x_add(sr, Lr); sg = x_add(sg, Lg); sb = x_add(sb, Lb);
+                s++;
+                left = 0;
+                if (s == pr.spp) {  // pixel finished (main.rs:78-81)
+                    const size_t off = ((size_t)(py - pr.out_row0) * pr.width + px) * 3;
+                    pr.out[off + 0] = (uint8_t)quantise(sr, spp_f);
+                    pr.out[off + 1] = (uint8_t)quantise(sg, spp_f);
+                    pr.out[off + 2] = (uint8_t)quantise(sb, spp_f);
+                    have_px = false;
+                }
+            }
+        }
+    }
+
+    ctr.v[CTR_RAYS] = rays;
+#pragma unroll
+    for (int i = 0; i < NUM_COUNTERS; i++) {
+        if (!COUNT && i != CTR_RAYS) continue;
+        unsigned long long v = ctr.v[i];
+#pragma unroll
+        for (int ofs = 16; ofs > 0; ofs >>= 1) v += __shfl_down_sync(FULL, v, ofs);
+        if (lane == 0 && v) atomicAdd(&pr.counters[i], v);
+    }
+}
+
 }  // namespace rtb
 #include "rt_kernel_sched.cuh"
+#include "rt_kernel_deferred.cuh"
 namespace rtb {
 
 // ---------------------------------------------------------------------------------------------
@@ -523,30 +877,46 @@ template <int ISECT, bool SMEM>
 static KernelFn pick_count(bool count) {
     return count ? (KernelFn)render_kernel<ISECT, SMEM, true> : (KernelFn)render_kernel<ISECT, SMEM, false>;
 }
-// RT_B200_BVH_KERNEL=simple selects the first (unscheduled) BVH megakernel, kept for A/B measurements
-static bool use_sched_kernel() {
+// RT_B200_BVH_KERNEL = lanes (default) | simple | pools | deferred : megakernel variant, kept selectable for A/B runs
+static int bvh_variant() {
     static int v = -1;
     if (v < 0) {
         const char* e = std::getenv("RT_B200_BVH_KERNEL");
-        v = (e && std::strcmp(e, "simple") == 0) ? 0 : 1;
+        v = 3;
+        if (e && std::strcmp(e, "simple") == 0) v = 0;
+        if (e && std::strcmp(e, "pools") == 0) v = 1;
+        if (e && std::strcmp(e, "deferred") == 0) v = 2;
     }
-    return v == 1;
+    return v;
+}
+static int env_int(const char* name, int dflt) {
+    const char* e = std::getenv(name);
+    return e ? std::atoi(e) : dflt;
+}
+#define RT_PICK_SCHED(KERNEL)                                                                                       \
+    do {                                                                                                            \
+        if (minb == 3) {                                                                                            \
+            if (smem) return count ? (KernelFn)KERNEL<true, true, 3> : (KernelFn)KERNEL<true, false, 3>;            \
+            return count ? (KernelFn)KERNEL<false, true, 3> : (KernelFn)KERNEL<false, false, 3>;                    \
+        }                                                                                                           \
+        if (smem) return count ? (KernelFn)KERNEL<true, true, 2> : (KernelFn)KERNEL<true, false, 2>;                \
+        return count ? (KernelFn)KERNEL<false, true, 2> : (KernelFn)KERNEL<false, false, 2>;                        \
+    } while (0)
+template <int ISECT, bool SMEM>
+static KernelFn pick_lanes(bool count) {
+    return count ? (KernelFn)render_kernel_lanes<ISECT, SMEM, true> : (KernelFn)render_kernel_lanes<ISECT, SMEM, false>;
 }
 static KernelFn pick_kernel(int isect, bool smem, bool count) {
-    if (isect == RT_INTERSECT_BRUTE) return smem ? pick_count<RT_INTERSECT_BRUTE, true>(count) : pick_count<RT_INTERSECT_BRUTE, false>(count);
-    if (use_sched_kernel()) {
-        static int minb = -1;  // RT_B200_SCHED_MINB=3 trades registers (<= 80) for 24 resident warps per SM
-        if (minb < 0) {
-            const char* e = std::getenv("RT_B200_SCHED_MINB");
-            minb = (e && std::atoi(e) == 3) ? 3 : 2;
-        }
-        if (minb == 3) {
-            if (smem) return count ? (KernelFn)render_kernel_sched<true, true, 3> : (KernelFn)render_kernel_sched<true, false, 3>;
-            return count ? (KernelFn)render_kernel_sched<false, true, 3> : (KernelFn)render_kernel_sched<false, false, 3>;
-        }
-        if (smem) return count ? (KernelFn)render_kernel_sched<true, true, 2> : (KernelFn)render_kernel_sched<true, false, 2>;
-        return count ? (KernelFn)render_kernel_sched<false, true, 2> : (KernelFn)render_kernel_sched<false, false, 2>;
+    if (bvh_variant() == 3) {
+        if (isect == RT_INTERSECT_BRUTE) return smem ? pick_lanes<RT_INTERSECT_BRUTE, true>(count) : pick_lanes<RT_INTERSECT_BRUTE, false>(count);
+        return smem ? pick_lanes<RT_INTERSECT_BVH, true>(count) : pick_lanes<RT_INTERSECT_BVH, false>(count);
     }
+    if (isect == RT_INTERSECT_BRUTE) return smem ? pick_count<RT_INTERSECT_BRUTE, true>(count) : pick_count<RT_INTERSECT_BRUTE, false>(count);
+    static int minb = -1;  // RT_B200_SCHED_MINB=3 trades registers (<= 80) for 24 resident warps per SM
+    if (minb < 0) minb = env_int("RT_B200_SCHED_MINB", 2) == 3 ? 3 : 2;
+    const int v = bvh_variant();
+    if (v == 2) RT_PICK_SCHED(render_kernel_deferred);
+    if (v == 1) RT_PICK_SCHED(render_kernel_sched);
     return smem ? pick_count<RT_INTERSECT_BVH, true>(count) : pick_count<RT_INTERSECT_BVH, false>(count);
 }
 
@@ -577,7 +947,20 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
     uint64_t grid = (uint64_t)sm_count * per_sm;
     if (grid > want_ctas) grid = want_ctas;
     if (grid < 1) grid = 1;
-    fn<<<(unsigned)grid, THREADS, dyn, stream>>>(sc, cam, pr);
+    DevParams prm = pr;
+    static int w[4] = {-1, 0, 0, 0}, nnum = 1, nden = 2;
+    if (w[0] < 0) {
+        w[0] = env_int("RT_B200_W_NODE", 1);
+        w[1] = env_int("RT_B200_W_LEAF", 1);
+        w[2] = env_int("RT_B200_W_HIT", 1);
+        w[3] = env_int("RT_B200_W_PRIM", 1);
+        nnum = env_int("RT_B200_NODE_NUM", 1);
+        nden = env_int("RT_B200_NODE_DEN", 2);
+    }
+    for (int i = 0; i < 4; i++) prm.sched_w[i] = w[i];
+    prm.sched_node_num = nnum;
+    prm.sched_node_den = nden;
+    fn<<<(unsigned)grid, THREADS, dyn, stream>>>(sc, cam, prm);
     if (info) {
         info->grid = (unsigned)grid;
         info->threads = THREADS;
