@@ -176,7 +176,7 @@ def run_reference(args, cfg, sp, tr):
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    return line
 
 
 def workload_config(args, cfg):
@@ -189,7 +189,16 @@ def workload_config(args, cfg):
 
 
 # --------------------------------------------------------------------------------------------------------
+def _claim_stdout():
+    """Keep fd 1 for the ONE JSON line: libraries (NCCL prints its version banner there) get stderr instead."""
+    sys.stdout.flush()
+    real = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+    return real
+
+
 def main():
+    real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -213,14 +222,15 @@ def main():
 
     if args.impl == "reference":
         if rank == 0:
-            run_reference(args, cfg, sp, tr)
+            real_stdout.write(json.dumps(run_reference(args, cfg, sp, tr)) + "\n")
+            real_stdout.flush()
         return 0
 
     if args.gpus > 1 and world == 1:
         # convenience: re-launch under torchrun
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={args.gpus}",
                "--master-addr", "127.0.0.1", "--master-port", "29517", os.path.abspath(__file__)] + sys.argv[1:]
-        return subprocess.call(cmd)
+        return subprocess.call(cmd, stdout=real_stdout.fileno())
 
     import torch
 
@@ -376,7 +386,8 @@ def main():
         }
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
-        print(json.dumps(line), flush=True)
+        real_stdout.write(json.dumps(line) + "\n")
+        real_stdout.flush()
     sched.close()
     scene.close()
     ctx.close()
