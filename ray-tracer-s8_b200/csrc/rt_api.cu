@@ -27,6 +27,7 @@ struct rt_ctx {
     unsigned long long* d_ctr = nullptr;  // NUM_COUNTERS counters + tile ticket (last slot)
     unsigned long long* h_ctr = nullptr;  // pinned mirror
     float* d_scratch = nullptr;
+    WaveBuffers wave;
     std::string err;
 };
 
@@ -125,6 +126,7 @@ void rt_shutdown(rt_ctx* ctx) {
     if (ctx->d_ctr) cudaFree(ctx->d_ctr);
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    free_wave_buffers(&ctx->wave);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -628,8 +630,13 @@ int launch(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, uint32_t row0,
     pr.tile_counter = reinterpret_cast<unsigned int*>(ctx->d_ctr + NUM_COUNTERS);
     CK(ctx, cudaMemsetAsync(ctx->d_ctr, 0, (NUM_COUNTERS + 1) * sizeof(unsigned long long), ctx->stream));
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    CK(ctx, launch_render(scene->dev, r.cam, pr, r.isect, r.p.collect_counters != 0, ctx->sm_count, ctx->smem_optin,
-                          ctx->stream, info));
+    if (use_wavefront(r.isect)) {
+        CK(ctx, launch_wavefront(scene->dev, r.cam, pr, r.p.collect_counters != 0, ctx->sm_count, ctx->smem_optin,
+                                 ctx->stream, &ctx->wave, info));
+    } else {
+        CK(ctx, launch_render(scene->dev, r.cam, pr, r.isect, r.p.collect_counters != 0, ctx->sm_count,
+                              ctx->smem_optin, ctx->stream, info));
+    }
     CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
     return RT_OK;
 }
@@ -664,7 +671,7 @@ int finish_stats(rt_ctx* ctx, const Resolved& r, uint64_t pixels, rt_stats* st,
     st->kernel_ms = ms;
     st->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     st->intersector_used = (uint32_t)r.isect;
-    st->kernel_launches = 1;
+    st->kernel_launches = li.launches;
     st->grid_ctas = li.grid;
     st->cta_threads = li.threads;
     st->ctas_per_sm = (uint32_t)li.ctas_per_sm;

@@ -19,9 +19,25 @@ struct LaunchInfo {
     size_t dyn_smem = 0;
     int ctas_per_sm = 0;
     bool scene_in_smem = false;
+    unsigned launches = 1;
 };
 
+// device buffers of the wavefront pipeline (owned by the context, grown on demand)
+struct WaveBuffers {
+    void* slots = nullptr;          // WSlot[capacity]
+    uint32_t* q_ray = nullptr;      // [capacity] each
+    uint32_t* q_hit = nullptr;
+    uint32_t* q_miss = nullptr;
+    uint32_t* path_ext = nullptr;   // [(ext_depth) * capacity] path entries beyond the 8 kept in the slot
+    void* counters = nullptr;       // WaveCounters[2]
+    size_t capacity = 0, ext_entries = 0;
+};
+void free_wave_buffers(WaveBuffers* wb);
+
 // rt_kernels.cu
+cudaError_t launch_wavefront(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
+                             int smem_optin, cudaStream_t stream, WaveBuffers* wb, LaunchInfo* info);
+bool use_wavefront(int isect);
 cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevParams& pr, int isect, bool count,
                           int sm_count, int smem_optin, cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_fp32_peak(float* scratch, int sm_count, int iters, cudaStream_t stream);

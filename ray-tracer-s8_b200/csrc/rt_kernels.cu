@@ -18,6 +18,7 @@
 #include "rt_device.cuh"
 #include "rt_host.h"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -847,6 +848,7 @@ __global__ void __launch_bounds__(THREADS, 3) render_kernel_lanes(const DevScene
 }  // namespace rtb
 #include "rt_kernel_sched.cuh"
 #include "rt_kernel_deferred.cuh"
+#include "rt_wavefront.cuh"
 namespace rtb {
 
 // ---------------------------------------------------------------------------------------------
@@ -883,6 +885,7 @@ static int bvh_variant() {
     if (v < 0) {
         const char* e = std::getenv("RT_B200_BVH_KERNEL");
         v = 3;
+        if (e && std::strcmp(e, "wave") == 0) v = 4;
         if (e && std::strcmp(e, "simple") == 0) v = 0;
         if (e && std::strcmp(e, "pools") == 0) v = 1;
         if (e && std::strcmp(e, "deferred") == 0) v = 2;
@@ -967,6 +970,98 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
         info->dyn_smem = dyn;
         info->ctas_per_sm = per_sm;
         info->scene_in_smem = smem;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Wavefront driver
+// ---------------------------------------------------------------------------------------------
+bool use_wavefront(int isect) { return isect == RT_INTERSECT_BVH && bvh_variant() == 4; }
+
+void free_wave_buffers(WaveBuffers* wb) {
+    if (wb->slots) cudaFree(wb->slots);
+    if (wb->q_ray) cudaFree(wb->q_ray);
+    if (wb->q_hit) cudaFree(wb->q_hit);
+    if (wb->q_miss) cudaFree(wb->q_miss);
+    if (wb->path_ext) cudaFree(wb->path_ext);
+    if (wb->counters) cudaFree(wb->counters);
+    *wb = WaveBuffers();
+}
+
+cudaError_t launch_wavefront(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
+                             int smem_optin, cudaStream_t stream, WaveBuffers* wb, LaunchInfo* info) {
+    const uint64_t total_tiles = (uint64_t)pr.tiles_x * pr.tiles_y;
+    const uint64_t my_tiles = (total_tiles + pr.tile_ranks - 1) / pr.tile_ranks;
+    const size_t n_slots = (size_t)my_tiles * TILE_W * TILE_H;
+    if (n_slots > 0xfffffff0ull || pr.spp > 65535u) return cudaErrorInvalidValue;
+    const size_t ext_depth = pr.depth > 8 ? pr.depth - 8 : 0;
+    cudaError_t e;
+    if (wb->capacity < n_slots || wb->ext_entries < ext_depth * n_slots) {
+        cudaStreamSynchronize(stream);
+        free_wave_buffers(wb);
+        if ((e = cudaMalloc(&wb->slots, n_slots * sizeof(WSlot))) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&wb->q_ray, n_slots * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&wb->q_hit, n_slots * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&wb->q_miss, n_slots * 4)) != cudaSuccess) return e;
+        if (ext_depth && (e = cudaMalloc(&wb->path_ext, ext_depth * n_slots * 4)) != cudaSuccess) return e;
+        if ((e = cudaMalloc(&wb->counters, 2 * sizeof(WaveCounters))) != cudaSuccess) return e;
+        wb->capacity = n_slots;
+        wb->ext_entries = ext_depth * n_slots;
+    }
+    WSlot* slots = (WSlot*)wb->slots;
+    WaveCounters* cnt = (WaveCounters*)wb->counters;
+    if ((e = cudaMemsetAsync(cnt, 0, 2 * sizeof(WaveCounters), stream)) != cudaSuccess) return e;
+
+    DevParams prm = pr;
+    prm.sched_w[0] = env_int("RT_B200_WAVE_REFILL", 8);
+
+    // trace kernel: scene staged in shared memory when it fits
+    const size_t need = (size_t)sc.ns * 16 + (size_t)sc.nt * 64 + (size_t)sc.ni * 56;
+    const bool smem = need + 1024 <= (size_t)smem_optin;
+    typedef void (*TraceFn)(const DevScene, const DevParams, WSlot*, const uint32_t*, uint32_t*, uint32_t*, WaveCounters*, int);
+    TraceFn tfn = smem ? (count ? (TraceFn)wave_trace<true, true> : (TraceFn)wave_trace<true, false>)
+                       : (count ? (TraceFn)wave_trace<false, true> : (TraceFn)wave_trace<false, false>);
+    const size_t dyn = smem ? need : 0;
+    if ((e = cudaFuncSetAttribute(tfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn)) != cudaSuccess) return e;
+    int t_per_sm = 0, l_per_sm = 0;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&t_per_sm, tfn, 256, dyn)) != cudaSuccess) return e;
+    typedef void (*LogicFn)(const DevScene, const DevCamera, const DevParams, WSlot*, const uint32_t*, const uint32_t*,
+                            uint32_t*, uint32_t*, uint32_t, WaveCounters*, int);
+    LogicFn lfn = count ? (LogicFn)wave_logic<true> : (LogicFn)wave_logic<false>;
+    if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&l_per_sm, lfn, 256, 0)) != cudaSuccess) return e;
+    if (t_per_sm < 1) t_per_sm = 1;
+    if (l_per_sm < 1) l_per_sm = 1;
+    const unsigned t_grid = (unsigned)std::min<uint64_t>((uint64_t)sm_count * t_per_sm, (n_slots + 255) / 256);
+    const unsigned l_grid = (unsigned)std::min<uint64_t>((uint64_t)sm_count * l_per_sm, (n_slots + 255) / 256);
+
+    wave_init<<<(unsigned)std::min<uint64_t>((uint64_t)sm_count * 8, (n_slots + 255) / 256), 256, 0, stream>>>(
+        prm, slots, (uint32_t)n_slots, wb->q_miss, cnt);
+    // one round = one query of every live pixel; a pixel makes at most spp * depth queries, +1 round to finish
+    const uint64_t rounds = (uint64_t)pr.spp * pr.depth + 1;
+    unsigned launches = 1;
+    static unsigned int* h_flag = nullptr;
+    if (!h_flag) cudaMallocHost(&h_flag, sizeof(unsigned int));
+    for (uint64_t r = 0; r < rounds; r++) {
+        const int parity = (int)(r & 1);
+        lfn<<<l_grid, 256, 0, stream>>>(sc, cam, prm, slots, wb->q_hit, wb->q_miss, wb->q_ray, wb->path_ext,
+                                        (uint32_t)n_slots, cnt, parity);
+        launches++;
+        if (rounds > 160 && (r % 16) == 15) {  // long chains (reference defaults): stop when no ray is left
+            cudaMemcpyAsync(h_flag, &cnt[parity ^ 1].n_ray, sizeof(unsigned int), cudaMemcpyDeviceToHost, stream);
+            cudaStreamSynchronize(stream);
+            if (*h_flag == 0) break;
+        }
+        tfn<<<t_grid, 256, dyn, stream>>>(sc, prm, slots, wb->q_ray, wb->q_hit, wb->q_miss, cnt, parity);
+        launches++;
+    }
+    if (info) {
+        info->grid = t_grid;
+        info->threads = 256;
+        info->dyn_smem = dyn;
+        info->ctas_per_sm = t_per_sm;
+        info->scene_in_smem = smem;
+        info->launches = launches;
     }
     return cudaGetLastError();
 }
