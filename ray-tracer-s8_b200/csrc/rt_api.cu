@@ -236,6 +236,19 @@ static int build_world_bvh(const rt_sphere* spheres, uint32_t n_spheres, const r
     return RT_OK;
 }
 
+// centre / half-extent form of a box (FILTER domain): t = (c - o)*inv -/+ h*|inv|.  h is padded for the rounding of
+// the c- and h-terms (<= 2^-24 * (2|c| + h) per axis); the o-term is covered per ray by the kernels.
+static void centre_half_of(const Box& b, float c[3], float h[3]) {
+    double m = 0.0;
+    for (int a = 0; a < 3; a++) m = std::fmax(m, std::fmax(std::fabs((double)b.min[a]), std::fabs((double)b.max[a])));
+    for (int a = 0; a < 3; a++) {
+        const double cc = 0.5 * ((double)b.min[a] + (double)b.max[a]);
+        const double hh = 0.5 * ((double)b.max[a] - (double)b.min[a]);
+        c[a] = (float)cc;
+        h[a] = (float)(hh * (1.0 + 4e-6) + 2e-6 * m + 1e-30);
+    }
+}
+
 int rt_bvh_build_host(const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles, uint32_t n_triangles,
                       const uint32_t* world_index, uint32_t* rank_out, uint32_t* n_nodes, uint32_t* depth) {
     const uint64_t n64 = (uint64_t)n_spheres + n_triangles;
@@ -406,13 +419,20 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         cc[0] = rc[2]; cc[1] = rhh[0]; cc[2] = rhh[1]; cc[3] = rhh[2];
     }
 
-    // ---- collapsed tree for the lanes kernel: subtrees of <= L same-kind primitives become one leaf ----
+    // ---- the lanes kernel's tree.  RT_B200_TREE=sah: cull with a 3-axis binned-SAH tree instead of the reference's
+    //      single-axis 6-bucket tree (ties still follow the reference tree's DFS ranks).  RT_B200_LEAF=L collapses
+    //      subtrees of <= L same-kind primitives into one leaf (only with the reference tree, whose DFS order = pid order).
     uint32_t lni = 0;
     int32_t lroot = 0;
     {
-        int L = 1;  // RT_B200_LEAF: primitives per leaf (1..32). Measured on C3: 1 → 51.8 ms, 4 → 54.6, 16 → 62.7 (profiles/)
+        const char* te = std::getenv("RT_B200_TREE");
+        HostBVH sah;
+        bool use_sah = te && std::strcmp(te, "sah") == 0;
+        if (use_sah) use_sah = build_bvh_sah(boxes, &sah) && sah.depth <= (uint32_t)MAX_STACK;
+        const HostBVH& T = use_sah ? sah : bvh;
+        int L = 1;  // measured on C3 (reference tree): 1 → 51.8 ms, 4 → 54.6, 16 → 62.7 (profiles/)
         if (const char* e = std::getenv("RT_B200_LEAF")) L = std::atoi(e);
-        if (L < 1) L = 1;
+        if (L < 1 || use_sah) L = 1;
         if (L > 32) L = 32;
         struct Sub { uint32_t n_s, n_t, first_s, first_t; };
         auto leaf_sub = [&](int32_t code) {
@@ -422,18 +442,14 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         std::vector<Sub> sub(ni);
         auto sub_of = [&](int32_t code) { return code >= 0 ? sub[(size_t)code] : leaf_sub(code); };
         for (uint32_t i = ni; i-- > 0;) {  // pre-order: children have larger indices than their parent
-            const Sub a = sub_of(bvh.inner[i].left), b = sub_of(bvh.inner[i].right);
+            const Sub a = sub_of(T.inner[i].left), b = sub_of(T.inner[i].right);
             sub[i] = Sub{a.n_s + b.n_s, a.n_t + b.n_t, a.n_s ? a.first_s : b.first_s, a.n_t ? a.first_t : b.first_t};
         }
         float* la = (float*)(blob.data() + o_la);
         float* lb = (float*)(blob.data() + o_lb);
         float* lc = (float*)(blob.data() + o_lc);
         int32_t* ld = (int32_t*)(blob.data() + o_ld);
-        const float* ca = (const float*)(blob.data() + o_ca);
-        const float* cb = (const float*)(blob.data() + o_cb);
-        const float* cc = (const float*)(blob.data() + o_cc);
         auto leaf_code = [](uint32_t first, uint32_t count) { return ~(int32_t)((first << 5) | (count - 1)); };
-        // iterative emit (explicit stack): (original code, slot to patch)
         struct Item { int32_t code; uint32_t parent; int side; };
         std::vector<Item> todo;
         auto classify = [&](int32_t code, bool* is_leaf) -> int32_t {
@@ -447,22 +463,26 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             return 0;
         };
         bool root_leaf;
-        lroot = classify(bvh.root, &root_leaf);
+        lroot = classify(T.root, &root_leaf);
         if (!root_leaf) {
-            todo.push_back(Item{bvh.root, 0, -1});
+            todo.push_back(Item{T.root, 0, -1});
             while (!todo.empty()) {
                 const Item it = todo.back();
                 todo.pop_back();
                 const uint32_t me = lni++;
                 if (it.side < 0) lroot = (int32_t)me;
                 else ld[2 * (size_t)it.parent + it.side] = (int32_t)me;
-                const size_t src = (size_t)it.code;
-                for (int k = 0; k < 4; k++) {
-                    la[4 * (size_t)me + k] = ca[4 * src + k];
-                    lb[4 * (size_t)me + k] = cb[4 * src + k];
-                    lc[4 * (size_t)me + k] = cc[4 * src + k];
-                }
-                const int32_t kids[2] = {bvh.inner[src].left, bvh.inner[src].right};
+                const HostNode& hn = T.inner[(size_t)it.code];
+                float lcn[3], lhh[3], rcn[3], rhh[3];
+                centre_half_of(hn.box_l, lcn, lhh);
+                centre_half_of(hn.box_r, rcn, rhh);
+                float* pa = la + 4 * (size_t)me;
+                float* pb = lb + 4 * (size_t)me;
+                float* pc = lc + 4 * (size_t)me;
+                pa[0] = lcn[0]; pa[1] = lcn[1]; pa[2] = lcn[2]; pa[3] = lhh[0];
+                pb[0] = lhh[1]; pb[1] = lhh[2]; pb[2] = rcn[0]; pb[3] = rcn[1];
+                pc[0] = rcn[2]; pc[1] = rhh[0]; pc[2] = rhh[1]; pc[3] = rhh[2];
+                const int32_t kids[2] = {hn.left, hn.right};
                 for (int side = 1; side >= 0; side--) {  // push right first so the left subtree is numbered first
                     bool is_leaf;
                     const int32_t c = classify(kids[side], &is_leaf);
@@ -549,8 +569,9 @@ struct Resolved {
     int isect;
 };
 
-// Brute force wins below this many primitives (measured crossover)
-constexpr uint32_t kBruteMaxPrims = 96;
+// Brute force (K1) is picked only for tiny scenes: on the C5 sweep the BVH kernel already wins at 64 spheres
+// (0.152 ms vs 0.247 ms at 1080p), see profiles/r1_c5_sweep.log
+constexpr uint32_t kBruteMaxPrims = 16;
 
 int resolve(rt_ctx* ctx, const rt_scene* scene, const rt_params* in, Resolved* r) {
     if (!scene || !in) return set_err(ctx, RT_ERR_INVALID_ARG, "NULL scene or params");

@@ -12,6 +12,7 @@
 // and emits only inner nodes, children encoded as codes, in DFS pre-order.
 //
 // Build with -ffp-contract=off (no FMA contraction on the host either).
+#include <algorithm>
 #include <cmath>
 #include <cstring>
 #include <limits>
@@ -200,6 +201,127 @@ struct Builder {
 };
 
 }  // namespace
+
+// ---------------------------------------------------------------------------------------------------------
+// Traversal-quality tree: binned SAH over all three axes (16 bins), one primitive per leaf.  Used only to
+// CULL on the GPU (any conservative tree gives the reference's nearest hit; exact-distance ties are broken by
+// the DFS rank of the reference-topology tree, which is still built).  Leaves are codes ~index like above.
+// ---------------------------------------------------------------------------------------------------------
+namespace {
+struct SahBuilder {
+    const std::vector<Box>& boxes;
+    std::vector<uint32_t> idx;
+    std::vector<float> cen;  // 3 per primitive
+    HostBVH* out;
+    static constexpr int kBins = 16;
+
+    SahBuilder(const std::vector<Box>& b, HostBVH* o) : boxes(b), out(o) {
+        idx.resize(b.size());
+        cen.resize(3 * b.size());
+        for (size_t i = 0; i < b.size(); i++) {
+            idx[i] = (uint32_t)i;
+            for (int a = 0; a < 3; a++) cen[3 * i + a] = 0.5f * (b[i].min[a] + b[i].max[a]);
+        }
+    }
+    static float area(const Bounds& b) { return b.empty() ? 0.0f : b.area(); }
+
+    int32_t build(size_t lo, size_t hi, uint32_t depth) {
+        const size_t n = hi - lo;
+        if (n == 1) {
+            out->leaf_order.push_back(idx[lo]);
+            if (depth > out->depth) out->depth = depth;
+            return ~(int32_t)idx[lo];
+        }
+        float cmin[3], cmax[3];
+        for (int a = 0; a < 3; a++) { cmin[a] = std::numeric_limits<float>::infinity(); cmax[a] = -cmin[a]; }
+        for (size_t i = lo; i < hi; i++)
+            for (int a = 0; a < 3; a++) {
+                cmin[a] = fminf(cmin[a], cen[3 * idx[i] + a]);
+                cmax[a] = fmaxf(cmax[a], cen[3 * idx[i] + a]);
+            }
+        int best_axis = -1, best_split = 0;
+        float best_cost = std::numeric_limits<float>::infinity();
+        for (int a = 0; a < 3; a++) {
+            const float ext = cmax[a] - cmin[a];
+            if (!(ext > 0.0f)) continue;
+            Bounds bb[kBins];
+            size_t cnt[kBins] = {0};
+            for (auto& b : bb) b.clear();
+            const float scale = (float)kBins * (1.0f - 1e-6f) / ext;
+            for (size_t i = lo; i < hi; i++) {
+                int k = (int)((cen[3 * idx[i] + a] - cmin[a]) * scale);
+                k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+                cnt[k]++;
+                bb[k].join(boxes[idx[i]]);
+            }
+            Bounds racc;
+            racc.clear();
+            float rarea[kBins];
+            size_t rcnt[kBins];
+            size_t c = 0;
+            for (int k = kBins - 1; k > 0; k--) {
+                racc.join(bb[k]);
+                c += cnt[k];
+                rarea[k] = area(racc);
+                rcnt[k] = c;
+            }
+            Bounds lacc;
+            lacc.clear();
+            size_t lc = 0;
+            for (int k = 0; k < kBins - 1; k++) {
+                lacc.join(bb[k]);
+                lc += cnt[k];
+                if (lc == 0 || rcnt[k + 1] == 0) continue;
+                const float cost = (float)lc * area(lacc) + (float)rcnt[k + 1] * rarea[k + 1];
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = k; }
+            }
+        }
+        size_t mid;
+        if (best_axis < 0) {
+            mid = lo + n / 2;  // coincident centroids
+        } else {
+            const float ext = cmax[best_axis] - cmin[best_axis];
+            const float scale = (float)kBins * (1.0f - 1e-6f) / ext;
+            auto first = idx.begin() + lo, last = idx.begin() + hi;
+            auto it = std::stable_partition(first, last, [&](uint32_t p) {
+                int k = (int)((cen[3 * p + best_axis] - cmin[best_axis]) * scale);
+                k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
+                return k <= best_split;
+            });
+            mid = (size_t)(it - idx.begin());
+            if (mid == lo || mid == hi) mid = lo + n / 2;
+        }
+        const int32_t me = (int32_t)out->inner.size();
+        out->inner.push_back(HostNode{});
+        Bounds bl, br;
+        bl.clear();
+        br.clear();
+        for (size_t i = lo; i < mid; i++) bl.join(boxes[idx[i]]);
+        for (size_t i = mid; i < hi; i++) br.join(boxes[idx[i]]);
+        const int32_t l = build(lo, mid, depth + 1);
+        const int32_t r = build(mid, hi, depth + 1);
+        HostNode& nd = out->inner[me];
+        nd.box_l = bl.box();
+        nd.box_r = br.box();
+        nd.left = l;
+        nd.right = r;
+        return me;
+    }
+};
+}  // namespace
+
+bool build_bvh_sah(const std::vector<Box>& boxes, HostBVH* out) {
+    out->inner.clear();
+    out->leaf_order.clear();
+    out->depth = 0;
+    if (boxes.empty()) return false;
+    out->inner.reserve(boxes.size());
+    out->leaf_order.reserve(boxes.size());
+    SahBuilder b(boxes, out);
+    out->root = b.build(0, boxes.size(), 0);
+    out->node_count = (uint32_t)(out->inner.size() + out->leaf_order.size());
+    return true;
+}
 
 bool build_bvh(const std::vector<Box>& boxes, HostBVH* out, std::string* err) {
     out->inner.clear();

@@ -61,5 +61,7 @@ struct HostBVH {
 // boxes[i] = AABB of the primitive at world position i.  Returns false (with a message) when the
 // reference's build would panic or never terminate.
 bool build_bvh(const std::vector<Box>& boxes, HostBVH* out, std::string* err);
+// 3-axis, 16-bin SAH tree over the same primitives, for culling only (leaf order is NOT the reference's).
+bool build_bvh_sah(const std::vector<Box>& boxes, HostBVH* out);
 
 }  // namespace rtb

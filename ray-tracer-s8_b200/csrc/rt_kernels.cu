@@ -659,15 +659,141 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
     }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Primary-ray candidate lists.  Every camera ray of an 8x4 tile lies in a thin beam: it starts on the lens
+// disc (radius aperture/2 around the camera origin, camera.rs:110-115) and passes through the focal point of a
+// jittered pixel position (camera.rs:116-127), i.e. through a small patch of the sphere of radius
+// focus_distance.  With X0(l) = org + l*f*d0 the beam's centre line (d0 = centre direction of the patch), any
+// beam point satisfies |X - X0(l)| <= |1-l|*lr + l*Rp (Rp = patch radius).  A warp culls the scene against its
+// tile's beam once and its primary rays test only the survivors — no traversal for 57 % of the rays of the
+// BASELINE frames, and none at all for tiles that see only sky.  FILTER domain: the list is a conservative
+// superset; hits are still decided by the exact tests and consider().
+// ---------------------------------------------------------------------------------------------
+constexpr int LIST_CAP = 62;       // 16-bit entries: count + 62 pids = 128 bytes per list (shared memory is tight on C3)
+typedef unsigned short ListEntry;
+constexpr int LIST_BAD = 0xffff;  // list[0] when the tile has too many candidates or the beam is unusable
+
+struct Beam {
+    V3 org, d0;
+    float f, lr, rp, kappa;
+    bool ok;
+};
+
+__device__ __forceinline__ V3 cam_dir(const DevCamera& cam, float u, float v) {
+    const float tx = cam.llc[0] + u * cam.hor[0] + v * cam.ver[0] - cam.org[0];
+    const float ty = cam.llc[1] + u * cam.hor[1] + v * cam.ver[1] - cam.org[1];
+    const float tz = cam.llc[2] + u * cam.hor[2] + v * cam.ver[2] - cam.org[2];
+    const float r = rsqrtf(tx * tx + ty * ty + tz * tz);
+    return mk(tx * r, ty * r, tz * r);
+}
+
+__device__ __forceinline__ Beam tile_beam(const DevCamera& cam, const DevParams& pr, uint32_t x0, uint32_t y0) {
+    Beam b;
+    // pixel + jitter in [0,1): u spans [x0, x0+8]/u_den; rows y0..y0+3 ↔ y_cam = h-1-y, v spans [y_cam, y_cam+1]/v_den
+    const float u0 = (float)x0 / cam.u_den, u1 = (float)(x0 + TILE_W) / cam.u_den;
+    const float yc_hi = (float)(pr.height - y0), yc_lo = (float)(pr.height - y0) - (float)TILE_H;
+    const float v0 = yc_lo / cam.v_den, v1 = yc_hi / cam.v_den;
+    const V3 c00 = cam_dir(cam, u0, v0), c10 = cam_dir(cam, u1, v0), c01 = cam_dir(cam, u0, v1), c11 = cam_dir(cam, u1, v1);
+    V3 m = mk(c00.x + c10.x + c01.x + c11.x, c00.y + c10.y + c01.y + c11.y, c00.z + c10.z + c01.z + c11.z);
+    const float r = rsqrtf(m.x * m.x + m.y * m.y + m.z * m.z);
+    b.d0 = mk(m.x * r, m.y * r, m.z * r);
+    auto dist = [&](V3 c) {
+        const float dx = c.x - b.d0.x, dy = c.y - b.d0.y, dz = c.z - b.d0.z;
+        return sqrtf(dx * dx + dy * dy + dz * dz);
+    };
+    b.f = cam.focus;
+    b.rp = fabsf(cam.focus) * (fmaxf(fmaxf(dist(c00), dist(c10)), fmaxf(dist(c01), dist(c11))) * 1.05f + 1e-6f);
+    b.lr = fabsf(cam.lens_radius) * 1.01f + 1e-7f;
+    b.org = mk(cam.org[0], cam.org[1], cam.org[2]);
+    b.kappa = (b.lr + b.rp) / fabsf(cam.focus);
+    // the bound needs a finite forward beam; anything odd (NaN, focus <= 0, aperture comparable to focus) → no list
+    b.ok = (cam.focus > 0.0f) && (b.kappa < 0.45f) && (r > 0.0f) && (r < 1e30f);
+    return b;
+}
+
+// can a ball (centre c, radius rad) be touched by any ray of the beam?  (conservative)
+__device__ __forceinline__ bool beam_touches(const Beam& b, float cx, float cy, float cz, float rad) {
+    const float wx = cx - b.org.x, wy = cy - b.org.y, wz = cz - b.org.z;
+    const float sc = wx * b.d0.x + wy * b.d0.y + wz * b.d0.z;
+    const float w2 = wx * wx + wy * wy + wz * wz;
+    const float rho = sqrtf(fmaxf(w2 - sc * sc, 0.0f));
+    const float scp = fmaxf(sc, 0.0f);
+    const float lc = scp / b.f;
+    const float ext = (rad + fabsf(1.0f - lc) * b.lr + lc * b.rp) * 2.0f + 1e-4f * (1.0f + sqrtf(w2));
+    if (sc + ext < 0.0f) return false;  // entirely behind the lens
+    const float l1 = fmaxf(scp - ext, 0.0f) / b.f, l2 = (scp + ext) / b.f;
+    const float rmax = fmaxf(fabsf(1.0f - l1) * b.lr + l1 * b.rp, fabsf(1.0f - l2) * b.lr + l2 * b.rp);
+    return !(rho > rad + rmax + 1e-4f * (1.0f + sqrtf(w2)));  // NaN → keep
+}
+
+// Warp-cooperative: fill list[0] = count (or -1: too many / unusable beam), list[1..] = pids.
+__device__ __forceinline__ void build_tile_list(const DevScene& sc, const SceneView& sv, const DevCamera& cam,
+                                                const DevParams& pr, uint32_t x0, uint32_t y0, ListEntry* list) {
+    const unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const Beam b = tile_beam(cam, pr, x0, y0);
+    int count = b.ok ? 0 : -1;
+    const int n = (int)(sc.ns + sc.nt), ns = (int)sc.ns;
+    for (int base = 0; base < n && count >= 0; base += 32) {
+        const int pid = base + lane;
+        bool keep = false;
+        if (pid < ns) {
+            const float4 s = sv.sph[pid];
+            keep = beam_touches(b, s.x, s.y, s.z, sqrtf(s.w) * 1.0001f + 1e-6f);
+        } else if (pid < n) {
+            const int t = pid - ns;
+            const V3 a = ld3(sv.tri[4 * t]), ab = ld3(sv.tri[4 * t + 1]), ac = ld3(sv.tri[4 * t + 2]);
+            // ball around the vertex centroid
+            const float gx = a.x + (ab.x + ac.x) * (1.0f / 3.0f), gy = a.y + (ab.y + ac.y) * (1.0f / 3.0f),
+                        gz = a.z + (ab.z + ac.z) * (1.0f / 3.0f);
+            auto d2 = [&](float px, float py, float pz) { return (px - gx) * (px - gx) + (py - gy) * (py - gy) + (pz - gz) * (pz - gz); };
+            const float r2 = fmaxf(d2(a.x, a.y, a.z), fmaxf(d2(a.x + ab.x, a.y + ab.y, a.z + ab.z), d2(a.x + ac.x, a.y + ac.y, a.z + ac.z)));
+            keep = beam_touches(b, gx, gy, gz, sqrtf(r2) * 1.0001f + 1e-6f);
+        }
+        const unsigned m = __ballot_sync(FULL, keep);
+        const int add = __popc(m);
+        if (count + add > LIST_CAP) {
+            count = -1;
+        } else {
+            if (keep) list[1 + count + __popc(m & ((1u << lane) - 1u))] = (ListEntry)pid;
+            count += add;
+        }
+    }
+    if (lane == 0) list[0] = count < 0 ? (ListEntry)LIST_BAD : (ListEntry)count;
+    __syncwarp();
+}
+
+template <bool COUNT>
+__device__ __forceinline__ void trace_list(const DevScene& sc, const SceneView& sv, const ListEntry* list, V3 o, V3 d,
+                                           Hit& best, Ctr& ctr) {
+    best.pid = -1;
+    best.dist = 0.0f;
+    float cull = 1001.0f;
+    const int cnt = list[0], ns = (int)sc.ns;
+    for (int i = 0; i < cnt; i++) {
+        const int pid = list[1 + i];
+        if (pid < ns) {
+            test_sphere<COUNT>(sc, sv.sph[pid], pid, o, d, best, ctr);
+        } else {
+            if (COUNT) ctr.v[CTR_TRI_TEST]++;
+            if (triangle_filter(sv.tri, pid - ns, o, d, cull)) triangle_exact<COUNT>(sc, sv.tri, pid - ns, pid, o, d, best, ctr);
+        }
+        if (best.pid >= 0) cull = fmaf(best.dist, 1.00001f, 1e-6f);
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 // The megakernel, second form: lanes are independent workers.  A lane that finishes its pixel takes the
 // next pixel of the warp's current 8x4 tile (the warp pulls tiles from the global ticket counter) instead of
 // idling until the slowest pixel of the tile is done; every trip of the loop is one nearest-hit query.
 // ---------------------------------------------------------------------------------------------
-template <int ISECT, bool SMEM, bool COUNT>
-__global__ void __launch_bounds__(THREADS, 3) render_kernel_lanes(const DevScene sc, const DevCamera cam,
+template <int ISECT, bool SMEM, bool COUNT, bool LISTS, int MINB = 3>
+__global__ void __launch_bounds__(THREADS, MINB) render_kernel_lanes(const DevScene sc, const DevCamera cam,
                                                                 const DevParams pr) {
     extern __shared__ float4 smem_dyn[];
+    // per warp: candidate lists of its two most recent tiles (LISTS variant only; measured slower)
+    __shared__ ListEntry s_lists[LISTS ? WARPS : 1][2][LISTS ? LIST_CAP + 2 : 1];
     SceneView sv;
     if (SMEM) {
         float4* p = smem_dyn;
@@ -715,6 +841,12 @@ __global__ void __launch_bounds__(THREADS, 3) render_kernel_lanes(const DevScene
     uint32_t tile_next = TILE_W * TILE_H;  // warp-uniform tile cursor (exhausted)
     uint32_t tile_x0 = 0, tile_y0 = 0;
     bool tiles_left = true;
+    // primary-ray candidate lists: only for the BVH intersector on scenes small enough to cull per tile
+    const bool use_lists = LISTS && (ISECT == RT_INTERSECT_BVH) && (sc.ns + sc.nt <= (uint32_t)pr.list_max_prims);
+    int cur_list = 1;       // warp-uniform: list slot of the warp's current tile
+    int my_list = 0;        // per lane: list slot of this lane's pixel
+    bool list_ok = false;   //           ... and whether that slot still holds this pixel's tile
+    const int warp = threadIdx.x >> 5;
 
     for (;;) {
         // ---- hand out pixels: warp-cooperative, tile by tile ----
@@ -735,6 +867,13 @@ __global__ void __launch_bounds__(THREADS, 3) render_kernel_lanes(const DevScene
                 tile_x0 = (uint32_t)(g % pr.tiles_x) * TILE_W;
                 tile_y0 = pr.row0 + (uint32_t)(g / pr.tiles_x) * TILE_H;
                 tile_next = 0;
+                if (LISTS && use_lists) {
+                    cur_list ^= 1;
+                    // a lane still working on a pixel of the tile that owned this slot falls back to the BVH
+                    if (have_px && my_list == cur_list) list_ok = false;
+                    __syncwarp();
+                    build_tile_list(sc, sv, cam, pr, tile_x0, tile_y0, s_lists[warp][cur_list]);
+                }
             }
             const uint32_t avail = TILE_W * TILE_H - tile_next;
             const uint32_t my = __popc(want & lt_mask);
@@ -744,6 +883,8 @@ __global__ void __launch_bounds__(THREADS, 3) render_kernel_lanes(const DevScene
                 if (x < pr.width && y < pr.row1) {  // tiles on the right/bottom edge are partial
                     px = x; py = y;
                     have_px = true;
+                    my_list = cur_list;
+                    list_ok = use_lists;
                     rng.seed_from_u64(pr.seed + ((uint64_t)y * pr.width + x));
                     sr = sg = sb = 0.0f;
                     s = 0;
@@ -756,10 +897,12 @@ __global__ void __launch_bounds__(THREADS, 3) render_kernel_lanes(const DevScene
         if (__ballot_sync(FULL, have_px) == 0) break;
 
         if (have_px) {
+            bool primary = false;
             if (left == 0) {  // start sample s
                 primary_ray(cam, px, pr.height - py - 1, rng, &o, &d);  // y_cam = h - y - 1 (main.rs:71)
                 left = pr.depth;
                 np = 0;
+                primary = true;
             }
             // ---- one nearest-hit query (ray_color with depth > 0) ----
             rays++;
@@ -769,8 +912,18 @@ __global__ void __launch_bounds__(THREADS, 3) render_kernel_lanes(const DevScene
                 if (lane == (__ffs(am) - 1)) ctr.v[CTR_TOTAL_LANES] += 32;
             }
             Hit h;
-            if (ISECT == RT_INTERSECT_BRUTE) trace_brute<COUNT>(sc, sv, o, d, h, ctr);
-            else trace_bvh_ch<COUNT>(sc, sv, o, d, h, ctr);
+            if (ISECT == RT_INTERSECT_BRUTE) {
+                trace_brute<COUNT>(sc, sv, o, d, h, ctr);
+            } else {
+                if (LISTS) {
+                    const ListEntry* list = s_lists[warp][my_list];
+                    const bool by_list = primary && list_ok && list[0] != LIST_BAD;
+                    if (by_list) trace_list<COUNT>(sc, sv, list, o, d, h, ctr);
+                    else trace_bvh_ch<COUNT>(sc, sv, o, d, h, ctr);
+                } else {
+                    trace_bvh_ch<COUNT>(sc, sv, o, d, h, ctr);
+                }
+            }
 
             bool done;
             float Lr, Lg, Lb;
@@ -905,9 +1058,18 @@ static int env_int(const char* name, int dflt) {
         if (smem) return count ? (KernelFn)KERNEL<true, true, 2> : (KernelFn)KERNEL<true, false, 2>;                \
         return count ? (KernelFn)KERNEL<false, true, 2> : (KernelFn)KERNEL<false, false, 2>;                        \
     } while (0)
+static int list_max_prims() {  // RT_B200_LIST_MAX=N enables the per-tile primary-ray candidate lists up to N primitives
+    static int v = -1;
+    if (v < 0) v = env_int("RT_B200_LIST_MAX", 0);
+    return v;
+}
 template <int ISECT, bool SMEM>
 static KernelFn pick_lanes(bool count) {
-    return count ? (KernelFn)render_kernel_lanes<ISECT, SMEM, true> : (KernelFn)render_kernel_lanes<ISECT, SMEM, false>;
+    if (ISECT == RT_INTERSECT_BVH && list_max_prims() > 0 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, true>;
+    static int minb = -1;  // RT_B200_LANES_MINB=4: 64 registers, 32 resident warps per SM (experiment)
+    if (minb < 0) minb = env_int("RT_B200_LANES_MINB", 3);
+    if (minb == 4 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 4>;
+    return count ? (KernelFn)render_kernel_lanes<ISECT, SMEM, true, false> : (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false>;
 }
 static KernelFn pick_kernel(int isect, bool smem, bool count) {
     if (bvh_variant() == 3) {
@@ -933,9 +1095,13 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
                           int sm_count, int smem_optin, cudaStream_t stream, LaunchInfo* info) {
     const size_t static_smem = WARPS * TILE_W * TILE_H * 3 + 64;
     size_t need = scene_smem_bytes(sc, isect);
-    // keep at least two CTAs per SM when the scene is staged in shared memory
-    bool smem = need + static_smem <= (size_t)smem_optin && need <= 110 * 1024;
-    if (!smem && need + static_smem <= (size_t)smem_optin) smem = true;  // one big CTA per SM still beats L1 misses
+    // Stage the scene in shared memory only while three CTAs per SM still fit (measured on the C5 sweep: at 2048
+    // spheres the 147 KB copy leaves one CTA per SM and loses to the L1/L2 path; profiles/r1_c5_sweep.log).
+    static int smem_override = -2;  // RT_B200_SMEM=0|1 forces the choice (measurement only)
+    if (smem_override == -2) smem_override = env_int("RT_B200_SMEM", -1);
+    bool smem = (need + static_smem + 1024) * 3 <= (size_t)smem_optin;
+    if (smem_override == 0) smem = false;
+    if (smem_override == 1) smem = need + static_smem + 1024 <= (size_t)smem_optin;
     KernelFn fn = pick_kernel(isect, smem, count);
     size_t dyn = smem ? need : 0;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
@@ -963,6 +1129,7 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
     for (int i = 0; i < 4; i++) prm.sched_w[i] = w[i];
     prm.sched_node_num = nnum;
     prm.sched_node_den = nden;
+    prm.list_max_prims = list_max_prims();
     fn<<<(unsigned)grid, THREADS, dyn, stream>>>(sc, cam, prm);
     if (info) {
         info->grid = (unsigned)grid;

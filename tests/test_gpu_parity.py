@@ -117,6 +117,45 @@ def test_mixed_world_order_and_mesh(ctx, rt, O, isect):
     assert st["rays"] == ost["rays"]
 
 
+def test_large_scene_l2_resident_path(ctx, rt, O):
+    """6000 spheres + plane: geometry and BVH (430 KB) no longer fit shared memory → the L1/L2-resident kernel variant."""
+    sp, tr = rt.scenes.synthetic_spheres(6000, 12), rt.scenes.ground_plane()
+    ref, ost = O.render_frame(sp, tr, 200, 120, 2, 5, seed=3, want_stats=True)
+    sc = ctx.scene(sp, tr)
+    img, st = ctx.render_frame(sc, rt.make_params(200, 120, spp=2, max_bounces=5, seed=3), want_stats=True)
+    sc.close()
+    assert st["scene_in_smem"] == 0 and st["intersector_used"] == 2
+    assert_parity(img, ref)
+    assert st["rays"] == ost["rays"]
+
+
+def test_kernel_variants_agree(rt, O):
+    """The alternative pipelines kept for A/B measurements (RT_B200_BVH_KERNEL) render the same bytes.
+    The variant is read once per process, so each runs in its own interpreter."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, hashlib; sys.path.insert(0, 'ray-tracer-s8_b200'); import rt_b200 as rt; from rt_b200 import scenes;"
+        "ctx = rt.Context(0); sc = ctx.scene(scenes.synthetic_spheres(300, 5), scenes.ground_plane());"
+        "img = ctx.render_frame(sc, rt.make_params(160, 96, spp=3, max_bounces=5, seed=4, intersector=2));"
+        "print(hashlib.sha256(img.tobytes()).hexdigest())"
+    )
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    digests = {}
+    for variant in ("lanes", "simple", "pools", "deferred", "wave"):
+        env = dict(os.environ, RT_B200_BVH_KERNEL=variant)
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, (variant, out.stderr[-500:])
+        digests[variant] = out.stdout.strip().splitlines()[-1]
+    assert len(set(digests.values())) == 1, digests
+    import hashlib
+
+    ref, _ = O.render_frame(rt.scenes.synthetic_spheres(300, 5), rt.scenes.ground_plane(), 160, 96, 3, 5, seed=4)
+    assert hashlib.sha256(ref.tobytes()).hexdigest() == digests["lanes"]
+
+
 def test_camera_parameters_and_seeds(ctx, rt, O):
     sp, tr = rt.scenes.synthetic_spheres(64, 2), rt.scenes.ground_plane()
     cam = dict(cam_origin=(0.5, 0.25, 1.0), aperture=0.02, focus_distance=6.0, field_of_view=1.0, focal_length=1.5)
