@@ -307,13 +307,63 @@ __device__ __forceinline__ int triangle_bounds(const float4* tri, int tidx, V3 o
 // ---------------------------------------------------------------------------------------------
 // K1: brute force
 // ---------------------------------------------------------------------------------------------
+// The hot loop is the FILTER alone, 11 FMA-pipe instructions + compare + branch per sphere:
+//   oc = o - c (3 FADD, the reference's own first operation, so the exact path reuses it)
+//   bh = d.oc, oc2 = oc.oc (2 FMUL + 4 FFMA);  m = bh*bh + (r^2 - 0.99998*oc2) (2 FFMA)
+// m >= 0  <=>  the reference's discriminant 4*(bh^2 - (|oc|^2 - r^2)) is above -8e-5*|oc|^2 (~300 ulp of slack).
+// Everything else (roots behind the origin, exact roots, slab check, min_by) runs only for the few spheres that pass.
+template <bool COUNT>
+__device__ __noinline__ void brute_sphere_slow(const DevScene& sc, const float4 s, int pid, V3 o, V3 d, Hit& best,
+                                               Ctr& ctr) {
+    const V3 oc = mk(x_sub(o.x, s.x), x_sub(o.y, s.y), x_sub(o.z, s.z));
+    const float bh = fmaf(oc.z, d.z, fmaf(oc.y, d.y, oc.x * d.x));
+    const float oc2 = fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x));
+    if (bh > 0.0f && (oc2 - s.w) > 1e-4f * oc2) return;  // both roots behind the origin: not in [T_MIN, T_MAX)
+    if (COUNT) ctr.v[CTR_SPH_EXACT]++;
+    float t;
+    if (!sphere_root_exact(d, oc, s.w, &t)) return;
+    if (COUNT) ctr.v[CTR_SPH_HIT]++;
+    consider(sc, o, d, t, pid, best);
+}
+
+__device__ __forceinline__ float brute_margin(const float4 s, V3 o, V3 d) {
+    const float ocx = x_sub(o.x, s.x), ocy = x_sub(o.y, s.y), ocz = x_sub(o.z, s.z);
+    const float bh = fmaf(ocz, d.z, fmaf(ocy, d.y, ocx * d.x));
+    const float oc2 = fmaf(ocz, ocz, fmaf(ocy, ocy, ocx * ocx));
+    return fmaf(bh, bh, fmaf(oc2, -0.99998f, s.w));
+}
+
+// a group of 8 spheres in which at least one passed the filter: re-test each, run the slow path for those
+template <bool COUNT>
+__device__ __noinline__ void brute_group_slow(const DevScene& sc, const float4* sph, int first, int count, V3 o, V3 d,
+                                              Hit& best, Ctr& ctr) {
+#pragma unroll 1
+    for (int k = 0; k < count; k++) {
+        const float4 s = sph[first + k];
+        if (!(brute_margin(s, o, d) < 0.0f)) brute_sphere_slow<COUNT>(sc, s, first + k, o, d, best, ctr);
+    }
+}
+
 template <bool COUNT>
 __device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
     best.pid = -1;
     best.dist = 0.0f;
     const int ns = (int)sc.ns;
-#pragma unroll 4
-    for (int i = 0; i < ns; i++) test_sphere<COUNT>(sc, sv.sph[i], i, o, d, best, ctr);
+    // a non-finite ray makes the margins NaN, which fmaxf would drop: send such a ray through the slow path whole
+    const bool weird = !(isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(d.x) && isfinite(d.y) && isfinite(d.z));
+    int i = 0;
+    for (; i + 8 <= ns; i += 8) {
+        // 8 x (LDS.128 + 11 FMA-pipe instructions), one max-reduction, ONE branch
+        float m = brute_margin(sv.sph[i], o, d);
+#pragma unroll
+        for (int k = 1; k < 8; k++) m = fmaxf(m, brute_margin(sv.sph[i + k], o, d));
+        if (COUNT) ctr.v[CTR_SPH_TEST] += 8;
+        if (!(m < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, i, 8, o, d, best, ctr);
+    }
+    if (i < ns) {
+        if (COUNT) ctr.v[CTR_SPH_TEST] += ns - i;
+        brute_group_slow<COUNT>(sc, sv.sph, i, ns - i, o, d, best, ctr);
+    }
     const int nt = (int)sc.nt;
     for (int j = 0; j < nt; j++) test_triangle<COUNT>(sc, sv.tri, j, ns + j, o, d, best, ctr);
 }
