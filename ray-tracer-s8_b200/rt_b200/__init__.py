@@ -5,6 +5,8 @@
 `wire`   : the reference's JSON wire types (RenderInfo / RenderMeta / ImageSlice)
 `slave`  : mirror of the reference slave's worker() and HTTP shell on top of the GPU path
 `multi`  : tile scheduler over the GPUs of one box (torch.distributed plumbing)
+`obj`    : OBJ + MTL ingest as the controller does it (ray-tracer-controller/src/obj.rs)
+`controller` : mirror of the controller's /upload, /result, /poll on top of the GPU slave
 """
 from . import scenes  # noqa: F401
 from .api import (  # noqa: F401

@@ -369,3 +369,34 @@ def test_http_shell_end_to_end(rt, O):
     assert list(o.keys()) == ["division_no", "image", "id"] and o["division_no"] == 2 and o["id"] == meta.id
     ref, _ = O.render_rows(sp, None, O.make_params(48, 32, 4, 2, 2, 3))
     assert_parity(np.array(o["image"], dtype=np.uint8).reshape(8, 48, 3), ref)
+
+
+def test_controller_upload_to_jpeg_on_a_mesh(rt, O):
+    """f4 + f2: OBJ ++ MTL → /upload → 20 divisions on the GPU worker → /poll → JPEG; the stitched frame must be the
+    oracle's frame (compared through the JPEG, and exactly through the worker)."""
+    import io
+
+    from PIL import Image
+
+    from rt_b200 import controller, obj, slave, wire
+    from test_host import mesh_scene_obj
+
+    data, n = mesh_scene_obj()
+    tris = obj.build_world(data, n)
+    wk = slave.Worker(0, spp=4, max_bounces=4, seed=11)
+    try:
+        c = controller.Controller(worker=wk, width=320, height=180, divisions=20)
+        job = c.upload(data, n)
+        jpeg, is_img = c.poll(job)
+        assert is_img
+        assert wk.scene_uploads == 1
+        ref, _ = O.render_frame(None, tris, 320, 180, 4, 4, seed=11)
+        got = np.array(Image.open(io.BytesIO(jpeg)).convert("RGB"))
+        mse = float(((got.astype(np.float64) - ref) ** 2).mean())
+        assert 10 * np.log10(255.0 ** 2 / mse) > 30.0                       # JPEG(90) of the same frame
+        meta = wire.RenderMeta(180, 320, 20, "00000000-0000-4000-8000-00000000000a")
+        world = wire.World(np.zeros(0, wire.SPHERE_DTYPE), tris, np.arange(len(tris), dtype=np.uint32))
+        bands = [wk.render(wire.RenderInfo(world, meta, d)).image.reshape(9, 320, 3) for d in range(20)]
+        assert_parity(np.concatenate(bands, axis=0), ref)
+    finally:
+        wk.close()

@@ -214,3 +214,107 @@ def test_gloo_world2_frame_assembly(rt):
         p.join(timeout=60)
         assert p.exitcode == 0
     assert ok
+
+
+# ---------------------------------------------------------------------------------------------------
+# "next" rows of SURVEY §8f: OBJ ingest (f4) and the controller's job state machine (f2), host side only
+# ---------------------------------------------------------------------------------------------------
+def _icosphere(subdiv=1, radius=1.0, centre=(0.0, 0.0, -4.0)):
+    t = (1 + 5 ** 0.5) / 2
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t), (0, -1, -t), (0, 1, -t),
+         (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2), (10, 7, 6),
+         (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5), (2, 4, 11), (6, 2, 10), (8, 6, 7),
+         (9, 8, 1)]
+    v = [np.array(p, dtype=np.float64) / np.linalg.norm(p) for p in v]
+    for _ in range(subdiv):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            k = (min(a, b), max(a, b))
+            if k not in cache:
+                m = v[a] + v[b]
+                v.append(m / np.linalg.norm(m))
+                cache[k] = len(v) - 1
+            return cache[k]
+
+        for a, b, c in f:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        f = nf
+    return [tuple(np.array(centre) + radius * p) for p in v], f
+
+
+def mesh_scene_obj():
+    """An 80-triangle icosphere over a two-triangle floor, as OBJ ++ MTL bytes (two materials, two models)."""
+    from rt_b200 import obj
+
+    vs, fs = _icosphere(1, 1.2, (0.3, 0.1, -4.0))
+    body = obj.write_obj(vs, fs, "ball")
+    n = len(vs)
+    floor = "usemtl floor\n" + "".join(f"v {x} -1.5 {z}\n" for x, z in [(-30, -40), (-30, 10), (30, 10), (30, -40)])
+    floor += f"f {n + 1} {n + 2} {n + 3}\nf {n + 1} {n + 3} {n + 4}\n"
+    o = body + floor.encode()
+    m = b"newmtl ball\nKd 0.9 0.3 0.2\nNs 600\nnewmtl floor\nKd 0.5 0.5 0.55\nNs 50\n"
+    return o + m, len(o)
+
+
+def test_obj_ingest_matches_reference_rules(rt):
+    from rt_b200 import obj
+
+    data, n = mesh_scene_obj()
+    tr = obj.build_world(data, n)
+    assert len(tr) == 82
+    assert np.allclose(tr["albedo"][0], (0.9, 0.3, 0.2)) and tr["roughness"][0] == np.float32(600) / np.float32(1000)
+    assert np.allclose(tr["albedo"][-1], (0.5, 0.5, 0.55)) and tr["roughness"][-1] == np.float32(0.05)
+    assert np.all(tr["emission"] == 0)
+    # face index forms: v, v/vt/vn, negative (relative)
+    o = b"usemtl m\nv 0 0 -3\nv 1 0 -3\nv 0 1 -3\nv 1 1 -3\nf 1 2 3\nf 2/1/1 4/2/2 -2//3\n"
+    m = b"newmtl m\nKd 0.8 0.2 0.1\nNs 250\n"
+    t = obj.build_world(o + m, len(o))
+    assert t["a"].tolist() == [[0, 0, -3], [1, 0, -3]] and t["c"][1].tolist() == [0, 1, -3]
+    # a quad is NOT triangulated: the reference cuts the flat index list into triples (obj.rs:23-26)
+    q = b"usemtl m\nv 0 0 0\nv 1 0 0\nv 1 1 0\nv 0 1 0\nv 2 2 2\nv 3 3 3\nf 1 2 3 4\nf 5 6 1\n"
+    t = obj.build_world(q + m, len(q))
+    assert len(t) == 2 and t["a"][1].tolist() == [0, 1, 0] and t["b"][1].tolist() == [2, 2, 2]
+    with pytest.raises(obj.ObjError):
+        obj.build_world(b"v 0 0 0\nv 1 0 0\nv 0 1 0\nf 1 2 3\n", 36)       # no material: reference unwraps None
+    with pytest.raises(obj.ObjError):
+        obj.build_world(o + m, len(o) + len(m) + 5)
+
+
+class _FakeWorker:
+    """Stands in for rt_b200.slave.Worker on a CPU box: a slice whose bytes encode (division, position)."""
+
+    def render(self, info):
+        from rt_b200 import wire
+
+        m = info.render_meta
+        rows = m.height // m.divisions
+        img = np.full((rows, m.width, 3), info.division_no * 10, dtype=np.uint8)
+        return wire.ImageSlice(info.division_no, img.reshape(-1), m.id)
+
+
+def test_controller_job_state_machine(rt):
+    from PIL import Image
+    import io
+
+    from rt_b200 import controller, wire
+
+    data, n = mesh_scene_obj()
+    c = controller.Controller(worker=_FakeWorker(), width=64, height=40, divisions=4)
+    assert c.poll("nope") == (b"Invalid Uuid", False)
+    assert c.poll("123e4567-e89b-12d3-a456-426614174000") == (b"No such job", False)
+    job = c.upload(data, n)
+    jpeg, is_img = c.poll(job)
+    assert is_img and jpeg[:2] == b"\xff\xd8"
+    img = np.array(Image.open(io.BytesIO(jpeg)))
+    assert img.shape == (40, 64, 3) and abs(int(img[35, 5, 0]) - 30) <= 2 and abs(int(img[2, 5, 0]) - 0) <= 2
+    assert c.poll(job) == (b"No such job", False)                    # jobs are removed after the first poll
+    # partial results: the reference's progress text
+    c2 = controller.Controller(worker=None, width=64, height=40, divisions=4)
+    meta = wire.RenderMeta(40, 64, 4, "123e4567-e89b-12d3-a456-426614174000")
+    c2.jobs[meta.id] = {"meta": meta, "result": {}}
+    c2.result(wire.ImageSlice(2, np.zeros(10 * 64 * 3, np.uint8), meta.id))
+    assert c2.result(wire.ImageSlice(0, np.zeros(10 * 64 * 3, np.uint8), "00000000-0000-4000-8000-000000000009")) == controller.SAVED_TEXT
+    assert c2.poll(meta.id) == (b"Job not finished yet 1/4", False)
