@@ -343,7 +343,10 @@ def main():
         "bound": "fp32", "kernel": "render_kernel<%s>" % ("BVH" if cst["intersector_used"] == 2 else "BRUTE"),
         "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
         "peak_source": "measured live: FFMA-chain micro-benchmark (rt_measure_fp32_peak); MEASURED_PEAKS.json has no CUDA-core figure",
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of this
+        # kernel on this workload at 1 GPU (profiles/r1_k2_lanes_ncu_summary.txt); not re-measured live
+        "traffic": (5.907456e6 + 2.400256e6) if (args.workload == "C3" and world == 1) else None,
+        "traffic_unit": "bytes per launch (ncu)",
         "algorithmic_flops_per_launch": flops, "kernel_ms_avg": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
         "flops_per_ray": flops / max(1, cst["rays"]),
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9},

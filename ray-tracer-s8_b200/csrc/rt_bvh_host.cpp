@@ -74,6 +74,7 @@ struct Builder {
     const std::vector<Box>& boxes;
     std::vector<uint32_t> idx, tmp;
     std::vector<uint8_t> bucket_of;
+    std::vector<float> centre;  // AABB::center of every shape, computed once (same f32 operations every time)
     HostBVH* out;
     std::string* err;
     bool failed = false;
@@ -82,7 +83,11 @@ struct Builder {
         idx.resize(b.size());
         tmp.resize(b.size());
         bucket_of.resize(b.size());
-        for (size_t i = 0; i < b.size(); i++) idx[i] = (uint32_t)i;
+        centre.resize(3 * b.size());
+        for (size_t i = 0; i < b.size(); i++) {
+            idx[i] = (uint32_t)i;
+            centre_of(b[i], &centre[3 * i]);
+        }
     }
 
     void fail(const char* msg) {
@@ -107,10 +112,8 @@ struct Builder {
         all.clear();
         cent.clear();
         for (size_t i = lo; i < hi; i++) {
-            float c[3];
-            centre_of(boxes[idx[i]], c);
             all.join(boxes[idx[i]]);
-            cent.grow(c);
+            cent.grow(&centre[3 * (size_t)idx[i]]);
         }
         const int32_t me = (int32_t)out->inner.size();
         out->inner.push_back(HostNode{});
@@ -133,8 +136,7 @@ struct Builder {
             size_t cnt[kBuckets] = {0, 0, 0, 0, 0, 0};
             for (auto& b : bb) b.clear();
             for (size_t i = lo; i < hi; i++) {
-                float c[3];
-                centre_of(boxes[idx[i]], c);
+                const float* c = &centre[3 * (size_t)idx[i]];
                 const float rel = (c[axis] - cent.lo[axis]) / extent;
                 const float scaled = rel * ((float)kBuckets - 0.01f);
                 // `as usize`: truncate, saturate, NaN → 0

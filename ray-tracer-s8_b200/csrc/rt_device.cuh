@@ -73,6 +73,7 @@ struct DevParams {
     // scheduled kernels: pool weights (NODE, LEAF, HIT, PRIM) and the NODE phase's stay-in-loop share num/den
     int sched_w[4];
     int sched_node_num, sched_node_den;
+    int tile_order_reverse;      // 1: tickets walk the tile grid from the last tile to the first
     int list_max_prims;          // primary-ray candidate lists are built when the scene has at most this many primitives
 };
 

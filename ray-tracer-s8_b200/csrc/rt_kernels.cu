@@ -908,12 +908,15 @@ __global__ void __launch_bounds__(THREADS, MINB) render_kernel_lanes(const DevSc
                     if (lane == 0) k = atomicAdd(pr.tile_counter, 1u);
                     k = __shfl_sync(FULL, k, 0);
                 }
-                const uint64_t g = (uint64_t)k * pr.tile_ranks + (pr.tile_rank + k) % pr.tile_ranks;
+                uint64_t g = (uint64_t)k * pr.tile_ranks + (pr.tile_rank + k) % pr.tile_ranks;
                 if (!tiles_left || g >= total_tiles) {
                     tiles_left = false;
                     if (!have_px) finished = true;
                     break;
                 }
+                // hand the frame out bottom-up: rows near the ground (long paths) first, the sky rows, whose pixels are
+                // short and uniform, last — they fill the tail of the launch (profiles/r1_notes.md, 8-GPU scaling)
+                if (pr.tile_order_reverse) g = total_tiles - 1 - g;
                 tile_x0 = (uint32_t)(g % pr.tiles_x) * TILE_W;
                 tile_y0 = pr.row0 + (uint32_t)(g / pr.tiles_x) * TILE_H;
                 tile_next = 0;
@@ -1180,6 +1183,9 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
     prm.sched_node_num = nnum;
     prm.sched_node_den = nden;
     prm.list_max_prims = list_max_prims();
+    static int rev = -1;  // RT_B200_TILE_ORDER=topdown restores the first hand-out order
+    if (rev < 0) { const char* e = std::getenv("RT_B200_TILE_ORDER"); rev = (e && std::strcmp(e, "topdown") == 0) ? 0 : 1; }
+    prm.tile_order_reverse = rev;
     fn<<<(unsigned)grid, THREADS, dyn, stream>>>(sc, cam, prm);
     if (info) {
         info->grid = (unsigned)grid;
