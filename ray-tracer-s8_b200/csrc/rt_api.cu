@@ -7,6 +7,7 @@
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
+#include <algorithm>
 #include <cstring>
 #include <limits>
 #include <new>
@@ -424,11 +425,68 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     //      subtrees of <= L same-kind primitives into one leaf (only with the reference tree, whose DFS order = pid order).
     uint32_t lni = 0;
     int32_t lroot = 0;
+    std::vector<uint32_t> big_world;  // split layout: world positions of the primitives kept out of the tree
+    bool ltree = true;
     {
+        // RT_B200_TREE = split (default) | sah | ref.  ref: the reference-topology tree itself.  sah: a 3-axis binned-SAH
+        // tree over all primitives.  split: the primitives whose box area is a large share of the whole scene's go to a
+        // short list tested ahead of the traversal, and the 3-axis SAH tree covers the rest (measured: profiles/).
         const char* te = std::getenv("RT_B200_TREE");
+        int mode = 2;
+        if (te && std::strcmp(te, "ref") == 0) mode = 0;
+        if (te && std::strcmp(te, "sah") == 0) mode = 1;
         HostBVH sah;
-        bool use_sah = te && std::strcmp(te, "sah") == 0;
-        if (use_sah) use_sah = build_bvh_sah(boxes, &sah) && sah.depth <= (uint32_t)MAX_STACK;
+        bool use_sah = false;
+        if (mode == 2 && n > 1) {
+            auto area_of = [](const Box& b) {
+                const double sx = (double)b.max[0] - b.min[0], sy = (double)b.max[1] - b.min[1], sz = (double)b.max[2] - b.min[2];
+                return 2.0 * (sx * sy + sx * sz + sy * sz);
+            };
+            Box all = boxes[0];
+            for (uint32_t w = 1; w < n; w++)
+                for (int a = 0; a < 3; a++) {
+                    all.min[a] = fminf(all.min[a], boxes[w].min[a]);
+                    all.max[a] = fmaxf(all.max[a], boxes[w].max[a]);
+                }
+            const double thresh = area_of(all) * (1.0 / 16.0);
+            std::vector<std::pair<double, uint32_t>> cand;
+            for (uint32_t w = 0; w < n; w++) {
+                const double a = area_of(boxes[w]);
+                if (a > thresh && a > 0.0) cand.push_back({-a, w});
+            }
+            std::sort(cand.begin(), cand.end());
+            if (cand.size() > (size_t)MAX_BIG) cand.resize(MAX_BIG);
+            std::vector<uint8_t> is_big(n, 0);
+            for (auto& c : cand) {
+                big_world.push_back(c.second);
+                is_big[c.second] = 1;
+            }
+            std::sort(big_world.begin(), big_world.end());
+            std::vector<Box> rest;
+            std::vector<uint32_t> rest_world;
+            for (uint32_t w = 0; w < n; w++)
+                if (!is_big[w]) {
+                    rest.push_back(boxes[w]);
+                    rest_world.push_back(w);
+                }
+            if (rest.empty()) {
+                ltree = false;
+            } else {
+                use_sah = build_bvh_sah(rest, &sah) && sah.depth <= (uint32_t)MAX_STACK;
+                if (use_sah) {  // leaf codes: subset index → world position
+                    auto remap = [&](int32_t c) { return c >= 0 ? c : ~(int32_t)rest_world[(uint32_t)~c]; };
+                    for (auto& nd : sah.inner) {
+                        nd.left = remap(nd.left);
+                        nd.right = remap(nd.right);
+                    }
+                    sah.root = remap(sah.root);
+                } else {
+                    big_world.clear();  // fall back to the reference tree over everything
+                }
+            }
+        } else if (mode == 1) {
+            use_sah = build_bvh_sah(boxes, &sah) && sah.depth <= (uint32_t)MAX_STACK;
+        }
         const HostBVH& T = use_sah ? sah : bvh;
         int L = 1;  // measured on C3 (reference tree): 1 → 51.8 ms, 4 → 54.6, 16 → 62.7 (profiles/)
         if (const char* e = std::getenv("RT_B200_LEAF")) L = std::atoi(e);
@@ -439,9 +497,10 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             const uint32_t w = (uint32_t)~code, pid = pid_of_world[w];
             return world[w].kind == 0 ? Sub{1, 0, pid, 0} : Sub{0, 1, 0, pid};
         };
-        std::vector<Sub> sub(ni);
+        const uint32_t tni = (uint32_t)T.inner.size();
+        std::vector<Sub> sub(tni);
         auto sub_of = [&](int32_t code) { return code >= 0 ? sub[(size_t)code] : leaf_sub(code); };
-        for (uint32_t i = ni; i-- > 0;) {  // pre-order: children have larger indices than their parent
+        for (uint32_t i = tni; i-- > 0;) {  // pre-order: children have larger indices than their parent
             const Sub a = sub_of(T.inner[i].left), b = sub_of(T.inner[i].right);
             sub[i] = Sub{a.n_s + b.n_s, a.n_t + b.n_t, a.n_s ? a.first_s : b.first_s, a.n_t ? a.first_t : b.first_t};
         }
@@ -462,8 +521,8 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             *is_leaf = false;
             return 0;
         };
-        bool root_leaf;
-        lroot = classify(T.root, &root_leaf);
+        bool root_leaf = true;
+        if (ltree) lroot = classify(T.root, &root_leaf);
         if (!root_leaf) {
             todo.push_back(Item{T.root, 0, -1});
             while (!todo.empty()) {
@@ -525,6 +584,9 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     d.lnode_d = (const int2*)(sc->d_blob + o_ld);
     d.lni = lni;
     d.lroot = lroot;
+    d.ltree = ltree ? 1 : 0;
+    d.nbig = (uint32_t)big_world.size();
+    for (size_t i = 0; i < (size_t)MAX_BIG; i++) d.big_pid[i] = i < big_world.size() ? pid_of_world[big_world[i]] : 0u;
     d.mat = (const float4*)(sc->d_blob + o_mat);
     d.emis = (const float*)(sc->d_blob + o_em);
     d.rank = (const uint32_t*)(sc->d_blob + o_rank);

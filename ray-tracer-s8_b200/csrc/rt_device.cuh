@@ -17,6 +17,7 @@ namespace rtb {
 constexpr int TILE_W = 8;        // a warp renders an 8x4-pixel tile
 constexpr int TILE_H = 4;
 constexpr int MAX_STACK = 64;    // BVH traversal stack entries (host rejects deeper trees)
+constexpr int MAX_BIG = 8;      // primitives tested ahead of the traversal (split layout)
 constexpr int MAX_PATH = 64;     // max_bounces + 1 <= MAX_PATH
 constexpr float T_MIN = 0.001f;  // shapes/mod.rs:12
 constexpr float T_MAX = 1000.0f; // shapes/mod.rs:13
@@ -44,6 +45,12 @@ struct DevScene {
     const int2* lnode_d;
     uint32_t lni;          // inner nodes of the collapsed tree
     int lroot;             // its root code
+    // "split" traversal layout: the few primitives whose box is a large share of the scene's (a ground plane's two
+    // triangles) are kept out of the tree and tested first, so they neither inflate the upper boxes nor cost node
+    // visits; the tree then covers the remaining primitives only (ltree == 0: nothing remains, no traversal).
+    uint32_t nbig;
+    int ltree;
+    uint32_t big_pid[MAX_BIG];
     const float4* mat;     // [ns+nt] albedo rgb, roughness
     const float* emis;     // [ns+nt]
     const uint32_t* rank;  // [ns+nt] DFS leaf rank (exact-distance tie-break, shapes/mod.rs:177-182)

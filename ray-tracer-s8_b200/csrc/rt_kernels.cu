@@ -665,6 +665,18 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
     int sp = 0;
     int cur = sc.lroot;
     const int ns = (int)sc.ns;
+    // split layout: the large primitives first (their hits shorten everything that follows)
+    for (uint32_t i = 0; i < sc.nbig; i++) {
+        const int pid = (int)sc.big_pid[i];
+        if (pid < ns) {
+            test_sphere<COUNT>(sc, sv.sph[pid], pid, o, d, best, ctr);
+        } else {
+            if (COUNT) ctr.v[CTR_TRI_TEST]++;
+            if (triangle_filter(sv.tri, pid - ns, o, d, cull)) triangle_exact<COUNT>(sc, sv.tri, pid - ns, pid, o, d, best, ctr);
+        }
+        if (best.pid >= 0) cull = fmaf(best.dist, 1.00001f, 1e-6f);
+    }
+    if (!sc.ltree) return;
     for (;;) {
         while (cur >= 0) {
             const float4 a = sv.na[cur], b = sv.nb[cur], c = sv.nc[cur];
