@@ -29,6 +29,7 @@ struct rt_ctx {
     unsigned long long* h_ctr = nullptr;  // pinned mirror
     float* d_scratch = nullptr;
     WaveBuffers wave;
+    WqBuffers wq;
     std::string err;
 };
 
@@ -128,6 +129,7 @@ void rt_shutdown(rt_ctx* ctx) {
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     free_wave_buffers(&ctx->wave);
+    free_wq_buffers(&ctx->wq);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -713,7 +715,10 @@ int launch(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, uint32_t row0,
     pr.tile_counter = reinterpret_cast<unsigned int*>(ctx->d_ctr + NUM_COUNTERS);
     CK(ctx, cudaMemsetAsync(ctx->d_ctr, 0, (NUM_COUNTERS + 1) * sizeof(unsigned long long), ctx->stream));
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
-    if (use_wavefront(r.isect)) {
+    if (use_wq(r.isect, pr)) {
+        CK(ctx, launch_wq(scene->dev, r.cam, pr, r.p.collect_counters != 0, ctx->sm_count, ctx->smem_optin, ctx->stream,
+                          &ctx->wq, info));
+    } else if (use_wavefront(r.isect)) {
         CK(ctx, launch_wavefront(scene->dev, r.cam, pr, r.p.collect_counters != 0, ctx->sm_count, ctx->smem_optin,
                                  ctx->stream, &ctx->wave, info));
     } else {

@@ -34,6 +34,16 @@ struct WaveBuffers {
 };
 void free_wave_buffers(WaveBuffers* wb);
 
+// device buffer of the warp-private wavefront kernel: per-chain state (rt_kernel_wq.cuh), grown on demand
+struct WqBuffers {
+    void* state = nullptr;
+    size_t bytes = 0;
+};
+void free_wq_buffers(WqBuffers* b);
+bool use_wq(int isect, const DevParams& pr);
+cudaError_t launch_wq(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
+                      int smem_optin, cudaStream_t stream, WqBuffers* wb, LaunchInfo* info);
+
 // rt_kernels.cu
 cudaError_t launch_wavefront(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
                              int smem_optin, cudaStream_t stream, WaveBuffers* wb, LaunchInfo* info);

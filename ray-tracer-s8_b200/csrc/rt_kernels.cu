@@ -1067,6 +1067,7 @@ __global__ void __launch_bounds__(THREADS, MINB) render_kernel_lanes(const DevSc
 #include "rt_kernel_sched.cuh"
 #include "rt_kernel_deferred.cuh"
 #include "rt_wavefront.cuh"
+#include "rt_kernel_wq.cuh"
 namespace rtb {
 
 // ---------------------------------------------------------------------------------------------
@@ -1104,6 +1105,7 @@ static int bvh_variant() {
         const char* e = std::getenv("RT_B200_BVH_KERNEL");
         v = 3;
         if (e && std::strcmp(e, "wave") == 0) v = 4;
+        if (e && std::strcmp(e, "wq") == 0) v = 5;
         if (e && std::strcmp(e, "simple") == 0) v = 0;
         if (e && std::strcmp(e, "pools") == 0) v = 1;
         if (e && std::strcmp(e, "deferred") == 0) v = 2;
@@ -1137,7 +1139,7 @@ static KernelFn pick_lanes(bool count) {
     return count ? (KernelFn)render_kernel_lanes<ISECT, SMEM, true, false> : (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false>;
 }
 static KernelFn pick_kernel(int isect, bool smem, bool count) {
-    if (bvh_variant() == 3) {
+    if (bvh_variant() == 3 || bvh_variant() == 5) {
         if (isect == RT_INTERSECT_BRUTE) return smem ? pick_lanes<RT_INTERSECT_BRUTE, true>(count) : pick_lanes<RT_INTERSECT_BRUTE, false>(count);
         return smem ? pick_lanes<RT_INTERSECT_BVH, true>(count) : pick_lanes<RT_INTERSECT_BVH, false>(count);
     }
@@ -1297,6 +1299,87 @@ cudaError_t launch_wavefront(const DevScene& sc, const DevCamera& cam, const Dev
         info->ctas_per_sm = t_per_sm;
         info->scene_in_smem = smem;
         info->launches = launches;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Warp-private wavefront (rt_kernel_wq.cuh)
+// ---------------------------------------------------------------------------------------------
+bool use_wq(int isect, const DevParams& pr) {
+    return isect == RT_INTERSECT_BVH && bvh_variant() == 5 && pr.spp <= 65535u && pr.depth <= 255u;
+}
+
+void free_wq_buffers(WqBuffers* b) {
+    if (b->state) cudaFree(b->state);
+    *b = WqBuffers();
+}
+
+typedef void (*WqFn)(const DevScene, const DevCamera, const DevParams, const WqArgs);
+template <int NW>
+static WqFn pick_wq(bool smem, bool count) {
+    if (smem) return count ? (WqFn)render_kernel_wq<true, true, NW> : (WqFn)render_kernel_wq<true, false, NW>;
+    return count ? (WqFn)render_kernel_wq<false, true, NW> : (WqFn)render_kernel_wq<false, false, NW>;
+}
+
+cudaError_t launch_wq(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
+                      int smem_optin, cudaStream_t stream, WqBuffers* wb, LaunchInfo* info) {
+    static int nw = -1, chains = -1, min_active = -1, min_node = 24;
+    if (nw < 0) {
+        nw = env_int("RT_B200_WQ_WARPS", 24);
+        if (nw != 16 && nw != 24 && nw != 32) nw = 24;
+        chains = env_int("RT_B200_WQ_CHAINS", 128);
+        chains = std::max(32, std::min(WQ_MAX_CHAINS, (chains / 32) * 32));
+        min_active = env_int("RT_B200_WQ_MIN_ACTIVE", 20);
+        min_node = env_int("RT_B200_WQ_MIN_NODE", 24);
+    }
+    const size_t scene_bytes = (((size_t)sc.ns * 16 + (size_t)sc.nt * 64 + (size_t)sc.lni * 56) + 15) & ~(size_t)15;
+    const size_t pool_bytes = (size_t)nw * wq_warp_smem((uint32_t)chains);
+    const bool smem = scene_bytes + pool_bytes + 1024 <= (size_t)smem_optin;
+    const size_t dyn = pool_bytes + (smem ? scene_bytes : 0);
+    WqFn fn = nw == 16 ? pick_wq<16>(smem, count) : nw == 32 ? pick_wq<32>(smem, count) : pick_wq<24>(smem, count);
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
+    if (e != cudaSuccess) return e;
+    // one CTA per SM; fewer when the share of this rank has fewer pixels than the chains of a full grid
+    const uint64_t total_tiles = (uint64_t)pr.tiles_x * pr.tiles_y;
+    const uint64_t my_tiles = (total_tiles + pr.tile_ranks - 1) / pr.tile_ranks;
+    const uint64_t per_cta = (uint64_t)nw * chains / (TILE_W * TILE_H);  // tiles in flight per CTA
+    uint64_t grid = std::min<uint64_t>((uint64_t)sm_count, (my_tiles + per_cta - 1) / per_cta);
+    if (grid < 1) grid = 1;
+    const size_t n = (size_t)grid * nw * chains;
+    const size_t bytes = wq_state_bytes(n, pr.depth);
+    if (wb->bytes < bytes) {
+        cudaStreamSynchronize(stream);
+        free_wq_buffers(wb);
+        if ((e = cudaMalloc(&wb->state, bytes)) != cudaSuccess) return e;
+        wb->bytes = bytes;
+    }
+    DevParams prm = pr;
+    static int rev = -1;
+    if (rev < 0) { const char* o = std::getenv("RT_B200_TILE_ORDER"); rev = (o && std::strcmp(o, "topdown") == 0) ? 0 : 1; }
+    prm.tile_order_reverse = rev;
+    WqArgs wa;
+    wa.base = wb->state;
+    wa.n = n;
+    wa.chains = (uint32_t)chains;
+    wa.min_active = (uint32_t)min_active;
+    wa.min_node = (uint32_t)min_node;
+    static int ww[4] = {-1, 0, 0, 0};
+    if (ww[0] < 0) {
+        ww[0] = env_int("RT_B200_WQ_BURST", 2);
+        ww[1] = env_int("RT_B200_WQ_T_LEAF", 4);
+        ww[2] = env_int("RT_B200_WQ_T_PEND", 6);
+        ww[3] = env_int("RT_B200_WQ_T_FIN", 6);
+    }
+    wa.node_burst = ww[0]; wa.t_leaf = ww[1]; wa.t_pend = ww[2]; wa.t_fin = ww[3];
+    wa.scene_bytes = (uint32_t)scene_bytes;
+    fn<<<(unsigned)grid, nw * 32, dyn, stream>>>(sc, cam, prm, wa);
+    if (info) {
+        info->grid = (unsigned)grid;
+        info->threads = nw * 32;
+        info->dyn_smem = dyn;
+        info->ctas_per_sm = 1;
+        info->scene_in_smem = smem;
     }
     return cudaGetLastError();
 }

@@ -144,7 +144,7 @@ def test_kernel_variants_agree(rt, O):
     )
     root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
     digests = {}
-    for variant in ("lanes", "simple", "pools", "deferred", "wave"):
+    for variant in ("lanes", "simple", "pools", "deferred", "wave", "wq"):
         env = dict(os.environ, RT_B200_BVH_KERNEL=variant)
         out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, (variant, out.stderr[-500:])
