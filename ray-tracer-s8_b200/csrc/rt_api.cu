@@ -318,6 +318,9 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     const size_t o_ca = take((size_t)ni * 16), o_cb = take((size_t)ni * 16), o_cc = take((size_t)ni * 16);
     const size_t o_la = take((size_t)ni * 16), o_lb = take((size_t)ni * 16), o_lc = take((size_t)ni * 16);
     const size_t o_ld = take((size_t)ni * 8);
+    // brute-force kernel: spheres in pairs for the packed f32x2 filter, padded to a multiple of 8 spheres
+    const uint32_t ns8 = (n_spheres + 7u) & ~7u;
+    const size_t o_sph2 = take((size_t)ns8 * 16);
     std::vector<uint8_t> blob(off ? off : 256, 0);
     float* h_sph = (float*)(blob.data() + o_sph);
     float* h_tri = (float*)(blob.data() + o_tri);
@@ -560,6 +563,20 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     sc->n_nodes = bvh.node_count;
     sc->depth = bvh.depth;
     sc->rank_by_world = rank_of_world;
+    {   // pair j = spheres 2j, 2j+1: (-c0.x, -c1.x, -c0.y, -c1.y) | (-c0.z, -c1.z, r0^2, r1^2); pads can never pass
+        float* h2 = (float*)(blob.data() + o_sph2);
+        for (uint32_t j = 0; j < ns8 / 2; j++) {
+            for (uint32_t k = 0; k < 2; k++) {
+                const uint32_t pid = 2 * j + k;
+                const bool real = pid < n_spheres;
+                const float* g = h_sph + 4 * (size_t)pid;
+                h2[8 * (size_t)j + 0 + k] = real ? -g[0] : 0.0f;
+                h2[8 * (size_t)j + 2 + k] = real ? -g[1] : 0.0f;
+                h2[8 * (size_t)j + 4 + k] = real ? -g[2] : 0.0f;
+                h2[8 * (size_t)j + 6 + k] = real ? g[3] : -std::numeric_limits<float>::infinity();
+            }
+        }
+    }
     sc->blob_bytes = blob.size();
     cudaError_t e = cudaSetDevice(ctx->device);
     if (e == cudaSuccess) e = cudaMalloc(&sc->d_blob, blob.size());
@@ -573,6 +590,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     DevScene& d = sc->dev;
     d.sph = (const float4*)(sc->d_blob + o_sph);
     d.tri = (const float4*)(sc->d_blob + o_tri);
+    d.sph2 = (const float4*)(sc->d_blob + o_sph2);
     d.node_a = (const float4*)(sc->d_blob + o_na);
     d.node_b = (const float4*)(sc->d_blob + o_nb);
     d.node_c = (const float4*)(sc->d_blob + o_nc);

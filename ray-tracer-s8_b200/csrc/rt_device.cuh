@@ -30,6 +30,7 @@ constexpr float T_MAX = 1000.0f; // shapes/mod.rs:13
 struct DevScene {
     const float4* sph;     // [ns]    cx, cy, cz, r*r
     const float4* tri;     // [nt*4]  a | b-a | c-a | normalize_or_zero((a-b)x(a-c))
+    const float4* sph2;    // [ceil8(ns)] sphere pairs for the packed f32x2 filter: -c.x pair, -c.y pair | -c.z pair, r*r pair
     const float4* node_a;  // [ni]    l.min.xyz, l.max.x
     const float4* node_b;  // [ni]    l.max.yz,  r.min.xy
     const float4* node_c;  // [ni]    r.min.z,   r.max.xyz
@@ -97,6 +98,31 @@ __device__ __forceinline__ float x_sub(float a, float b) { return __fsub_rn(a, b
 __device__ __forceinline__ float x_mul(float a, float b) { return __fmul_rn(a, b); }
 __device__ __forceinline__ float x_div(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float x_sqrt(float a) { return __fsqrt_rn(a); }
+
+// Packed FP32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): one issue slot carries two FP32 operations, so an
+// issue-bound FILTER loop can fill the FMA pipe.  FILTER domain only.
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk2(float lo, float hi) {
+    f32x2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void upk2(f32x2 v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+    f32x2 r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+    f32x2 r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
 
 struct V3 {
     float x, y, z;

@@ -40,6 +40,7 @@ struct Ctr {
 
 // Shared-memory view of the geometry arrays (or the global pointers when SMEM == false)
 struct SceneView {
+    const float4* sph2;  // brute-force kernel only
     const float4* sph;
     const float4* tri;
     const float4* na;
@@ -351,18 +352,44 @@ __device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView&
     const int ns = (int)sc.ns;
     // a non-finite ray makes the margins NaN, which fmaxf would drop: send such a ray through the slow path whole
     const bool weird = !(isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(d.x) && isfinite(d.y) && isfinite(d.z));
+    // Packed pairs: two spheres per instruction — 3 FADD2 + 2 FMUL2 + 6 FFMA2 per PAIR (5.5 FMA-pipe issue slots per
+    // sphere instead of 11), two LDS.128 per pair, one FMNMX3 per pair, one branch per 16 spheres.  The FMA pipe still
+    // does 11 lane-operations per sphere, so the loop is bound by the pipe, not by issue (profiles/r1_notes.md).
+    const f32x2 ox2 = pk2(o.x, o.x), oy2 = pk2(o.y, o.y), oz2 = pk2(o.z, o.z);
+    const f32x2 dx2 = pk2(d.x, d.x), dy2 = pk2(d.y, d.y), dz2 = pk2(d.z, d.z);
+    const f32x2 kk2 = pk2(-0.99998f, -0.99998f);
+    auto pair_margin = [&](int j, float m) {
+        const float4 A = sv.sph2[2 * j], B = sv.sph2[2 * j + 1];
+        const f32x2 ocx = add2(ox2, pk2(A.x, A.y)), ocy = add2(oy2, pk2(A.z, A.w)), ocz = add2(oz2, pk2(B.x, B.y));
+        const f32x2 bh = fma2(ocz, dz2, fma2(ocy, dy2, mul2(ocx, dx2)));
+        const f32x2 oc2 = fma2(ocz, ocz, fma2(ocy, ocy, mul2(ocx, ocx)));
+        const f32x2 mm = fma2(bh, bh, fma2(oc2, kk2, pk2(B.z, B.w)));
+        float m_lo, m_hi;
+        upk2(mm, m_lo, m_hi);
+        return fmaxf(fmaxf(m, m_lo), m_hi);
+    };
+    const int ns8 = (ns + 7) & ~7;
+    const float NEG = -3.0e38f;
     int i = 0;
-    for (; i + 8 <= ns; i += 8) {
-        // 8 x (LDS.128 + 11 FMA-pipe instructions), one max-reduction, ONE branch
-        float m = brute_margin(sv.sph[i], o, d);
+    for (; i + 16 <= ns8; i += 16) {
+        float m0 = NEG, m1 = NEG;
 #pragma unroll
-        for (int k = 1; k < 8; k++) m = fmaxf(m, brute_margin(sv.sph[i + k], o, d));
-        if (COUNT) ctr.v[CTR_SPH_TEST] += 8;
-        if (!(m < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, i, 8, o, d, best, ctr);
+        for (int k = 0; k < 4; k++) {
+            m0 = pair_margin((i >> 1) + k, m0);
+            m1 = pair_margin((i >> 1) + 4 + k, m1);
+        }
+        if (COUNT) ctr.v[CTR_SPH_TEST] += min(16, ns - i);
+        if (!(fmaxf(m0, m1) < 0.0f) || weird) {
+            if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, i, min(8, ns - i), o, d, best, ctr);
+            if ((!(m1 < 0.0f) || weird) && i + 8 < ns) brute_group_slow<COUNT>(sc, sv.sph, i + 8, min(8, ns - i - 8), o, d, best, ctr);
+        }
     }
-    if (i < ns) {
+    if (i < ns8) {
+        float m0 = NEG;
+#pragma unroll
+        for (int k = 0; k < 4; k++) m0 = pair_margin((i >> 1) + k, m0);
         if (COUNT) ctr.v[CTR_SPH_TEST] += ns - i;
-        brute_group_slow<COUNT>(sc, sv.sph, i, ns - i, o, d, best, ctr);
+        if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, i, ns - i, o, d, best, ctr);
     }
     const int nt = (int)sc.nt;
     for (int j = 0; j < nt; j++) test_triangle<COUNT>(sc, sv.tri, j, ns + j, o, d, best, ctr);
@@ -478,6 +505,12 @@ __global__ void __launch_bounds__(THREADS) render_kernel(const DevScene sc, cons
         float4* p = smem_dyn;
         float4* s_sph = p;  p += sc.ns;
         float4* s_tri = p;  p += 4 * sc.nt;
+        float4* s_sph2 = p;  // brute force only: the pair-packed copy of the spheres
+        if (ISECT == RT_INTERSECT_BRUTE) {
+            const uint32_t ns8 = (sc.ns + 7u) & ~7u;
+            for (uint32_t i = threadIdx.x; i < ns8; i += THREADS) s_sph2[i] = __ldg(&sc.sph2[i]);
+        }
+        sv.sph2 = s_sph2;
         float4* s_na = p;   p += sc.ni;
         float4* s_nb = p;   p += sc.ni;
         float4* s_nc = p;   p += sc.ni;
@@ -495,6 +528,7 @@ __global__ void __launch_bounds__(THREADS) render_kernel(const DevScene sc, cons
         __syncthreads();
         sv.sph = s_sph; sv.tri = s_tri; sv.na = s_na; sv.nb = s_nb; sv.nc = s_nc; sv.nd = s_nd;
     } else {
+        sv.sph2 = sc.sph2;
         sv.sph = sc.sph; sv.tri = sc.tri; sv.na = sc.node_a; sv.nb = sc.node_b; sv.nc = sc.node_c; sv.nd = sc.node_d;
     }
 
@@ -861,6 +895,12 @@ __global__ void __launch_bounds__(THREADS, MINB) render_kernel_lanes(const DevSc
         float4* p = smem_dyn;
         float4* s_sph = p;  p += sc.ns;
         float4* s_tri = p;  p += 4 * sc.nt;
+        float4* s_sph2 = p;  // brute force only: the pair-packed copy of the spheres
+        if (ISECT == RT_INTERSECT_BRUTE) {
+            const uint32_t ns8 = (sc.ns + 7u) & ~7u;
+            for (uint32_t i = threadIdx.x; i < ns8; i += THREADS) s_sph2[i] = __ldg(&sc.sph2[i]);
+        }
+        sv.sph2 = s_sph2;
         float4* s_na = p;   p += sc.ni;
         float4* s_nb = p;   p += sc.ni;
         float4* s_nc = p;   p += sc.ni;
@@ -878,6 +918,7 @@ __global__ void __launch_bounds__(THREADS, MINB) render_kernel_lanes(const DevSc
         __syncthreads();
         sv.sph = s_sph; sv.tri = s_tri; sv.na = s_na; sv.nb = s_nb; sv.nc = s_nc; sv.nd = s_nd;
     } else {
+        sv.sph2 = sc.sph2;
         sv.sph = sc.sph; sv.tri = sc.tri; sv.na = sc.lnode_a; sv.nb = sc.lnode_b; sv.nc = sc.lnode_c; sv.nd = sc.lnode_d;
     }
 
@@ -1155,6 +1196,7 @@ static KernelFn pick_kernel(int isect, bool smem, bool count) {
 size_t scene_smem_bytes(const DevScene& sc, int isect) {
     size_t b = (size_t)sc.ns * 16 + (size_t)sc.nt * 64;
     if (isect == RT_INTERSECT_BVH) b += (size_t)sc.ni * (48 + 8);
+    else b += (size_t)((sc.ns + 7u) & ~7u) * 16;  // pair-packed spheres
     return b;
 }
 
