@@ -340,7 +340,7 @@ def main():
     achieved = flops / (k_ms * 1e-3) / 1e12
     alg_bytes = scene_bytes + (pixels // world) * 3
     roofline = {
-        "bound": "fp32", "kernel": "render_kernel<%s>" % ("BVH" if cst["intersector_used"] == 2 else "BRUTE"),
+        "bound": "fp32", "kernel": "render_kernel_lanes<%s>" % ("BVH" if cst["intersector_used"] == 2 else "BRUTE"),
         "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
         "peak_source": "measured live: FFMA-chain micro-benchmark (rt_measure_fp32_peak); MEASURED_PEAKS.json has no CUDA-core figure",
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of this

@@ -30,12 +30,18 @@ struct rt_ctx {
     float* d_scratch = nullptr;
     WaveBuffers wave;
     WqBuffers wq;
+    // scene upload: one pinned staging buffer the blob is assembled in, and a few retired device blobs kept for the
+    // next rt_scene_create (a slave makes one scene per job: cudaMalloc/cudaFree per job were a third of a small job)
+    uint8_t* h_stage = nullptr;
+    size_t h_stage_bytes = 0;
+    struct Retired { uint8_t* p; size_t cap; };
+    std::vector<Retired> retired;
     std::string err;
 };
 
 struct rt_scene {
     uint8_t* d_blob = nullptr;
-    size_t blob_bytes = 0;
+    size_t blob_bytes = 0, blob_cap = 0;
     DevScene dev{};
     uint32_t n = 0, n_nodes = 0, depth = 0;
     std::vector<uint32_t> rank_by_world;  // world position → DFS leaf rank
@@ -130,6 +136,9 @@ void rt_shutdown(rt_ctx* ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     free_wave_buffers(&ctx->wave);
     free_wq_buffers(&ctx->wq);
+    for (auto& r : ctx->retired) cudaFree(r.p);
+    ctx->retired.clear();
+    if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -286,6 +295,15 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     if ((n_spheres && !spheres) || (n_triangles && !triangles))
         return set_err(ctx, RT_ERR_INVALID_ARG, "rt_scene_create: NULL primitive array");
     const uint32_t n = (uint32_t)n64;
+    // RT_B200_TIMING=1: stage times of this call on stderr (development aid)
+    static const bool timing = std::getenv("RT_B200_TIMING") != nullptr;
+    auto t_prev = std::chrono::steady_clock::now();
+    auto lap = [&](const char* what) {
+        if (!timing) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[rt_scene_create n=%u] %-22s %8.3f ms\n", n, what, std::chrono::duration<double, std::milli>(now - t_prev).count());
+        t_prev = now;
+    };
     std::vector<PrimRef> world;
     std::vector<Box> boxes;  // the reference's (unpadded) shape AABBs by world position
     HostBVH bvh;
@@ -303,6 +321,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         pid_of_world[w] = world[w].kind == 0 ? next_s++ : next_t++;
     }
     const uint32_t ni = (uint32_t)bvh.inner.size();
+    lap("reference-tree build");
 
     // blob layout (each section 256-byte aligned)
     size_t off = 0;
@@ -311,17 +330,37 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         off = align_up(off + bytes, 256);
         return o;
     };
+    // The reference-topology node arrays (node_*, cnode_*) feed only the kernels kept for A/B runs
+    // (RT_B200_BVH_KERNEL=simple|pools|deferred|wave); the product kernels read the lnode_* tree.
+    const bool legacy = legacy_node_arrays_needed();
+    const size_t nl = legacy ? (size_t)ni : 0;
     const size_t o_sph = take((size_t)n_spheres * 16), o_tri = take((size_t)n_triangles * 64);
-    const size_t o_na = take((size_t)ni * 16), o_nb = take((size_t)ni * 16), o_nc = take((size_t)ni * 16);
-    const size_t o_nd = take((size_t)ni * 8), o_mat = take((size_t)n * 16), o_em = take((size_t)n * 4);
+    const size_t o_na = take(nl * 16), o_nb = take(nl * 16), o_nc = take(nl * 16);
+    const size_t o_nd = take(nl * 8), o_mat = take((size_t)n * 16), o_em = take((size_t)n * 4);
     const size_t o_rank = take((size_t)n * 4), o_box = take((size_t)n * 32);
-    const size_t o_ca = take((size_t)ni * 16), o_cb = take((size_t)ni * 16), o_cc = take((size_t)ni * 16);
+    const size_t o_ca = take(nl * 16), o_cb = take(nl * 16), o_cc = take(nl * 16);
     const size_t o_la = take((size_t)ni * 16), o_lb = take((size_t)ni * 16), o_lc = take((size_t)ni * 16);
     const size_t o_ld = take((size_t)ni * 8);
     // brute-force kernel: spheres in pairs for the packed f32x2 filter, padded to a multiple of 8 spheres
     const uint32_t ns8 = (n_spheres + 7u) & ~7u;
     const size_t o_sph2 = take((size_t)ns8 * 16);
-    std::vector<uint8_t> blob(off ? off : 256, 0);
+    struct Stage {  // the blob, assembled in the context's pinned staging buffer
+        uint8_t* p;
+        size_t n;
+        uint8_t* data() const { return p; }
+        size_t size() const { return n; }
+    } blob{nullptr, off ? off : 256};
+    if (ctx->h_stage_bytes < blob.n) {
+        CK(ctx, cudaSetDevice(ctx->device));
+        if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+        ctx->h_stage = nullptr;
+        ctx->h_stage_bytes = 0;
+        const size_t cap = align_up(blob.n + blob.n / 2, 1 << 16);
+        CK(ctx, cudaMallocHost(&ctx->h_stage, cap));
+        ctx->h_stage_bytes = cap;
+    }
+    blob.p = ctx->h_stage;
+    memset(blob.p, 0, blob.n);
     float* h_sph = (float*)(blob.data() + o_sph);
     float* h_tri = (float*)(blob.data() + o_tri);
     float* h_na = (float*)(blob.data() + o_na);
@@ -389,7 +428,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             hi[a] = b.max[a] + pad;
         }
     };
-    for (uint32_t i = 0; i < ni; i++) {
+    for (uint32_t i = 0; legacy && i < ni; i++) {
         const HostNode& hn = bvh.inner[i];
         float ll[3], lh[3], rl[3], rh[3];
         padded(hn.box_l, ll, lh);
@@ -425,6 +464,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         cc[0] = rc[2]; cc[1] = rhh[0]; cc[2] = rhh[1]; cc[3] = rhh[2];
     }
 
+    lap("primitive + node arrays");
     // ---- the lanes kernel's tree.  RT_B200_TREE=sah: cull with a 3-axis binned-SAH tree instead of the reference's
     //      single-axis 6-bucket tree (ties still follow the reference tree's DFS ranks).  RT_B200_LEAF=L collapses
     //      subtrees of <= L same-kind primitives into one leaf (only with the reference tree, whose DFS order = pid order).
@@ -557,6 +597,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         }
     }
 
+    lap("traversal tree");
     rt_scene* sc = new (std::nothrow) rt_scene();
     if (!sc) return set_err(ctx, RT_ERR_INVALID_ARG, "out of host memory");
     sc->n = n;
@@ -579,7 +620,19 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     }
     sc->blob_bytes = blob.size();
     cudaError_t e = cudaSetDevice(ctx->device);
-    if (e == cudaSuccess) e = cudaMalloc(&sc->d_blob, blob.size());
+    {   // smallest retired device blob that fits, else a new allocation
+        size_t pick = ctx->retired.size();
+        for (size_t i = 0; i < ctx->retired.size(); i++)
+            if (ctx->retired[i].cap >= blob.size() && (pick == ctx->retired.size() || ctx->retired[i].cap < ctx->retired[pick].cap)) pick = i;
+        if (pick < ctx->retired.size()) {
+            sc->d_blob = ctx->retired[pick].p;
+            sc->blob_cap = ctx->retired[pick].cap;
+            ctx->retired.erase(ctx->retired.begin() + (long)pick);
+        } else if (e == cudaSuccess) {
+            sc->blob_cap = align_up(blob.size(), 1 << 16);
+            e = cudaMalloc(&sc->d_blob, sc->blob_cap);
+        }
+    }
     if (e == cudaSuccess) e = cudaMemcpyAsync(sc->d_blob, blob.data(), blob.size(), cudaMemcpyHostToDevice, ctx->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) {
@@ -587,6 +640,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         delete sc;
         return set_err(ctx, RT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
     }
+    lap("upload");
     DevScene& d = sc->dev;
     d.sph = (const float4*)(sc->d_blob + o_sph);
     d.tri = (const float4*)(sc->d_blob + o_tri);
@@ -625,7 +679,10 @@ void rt_scene_destroy(rt_ctx* ctx, rt_scene* scene) {
         cudaSetDevice(ctx->device);
         cudaStreamSynchronize(ctx->stream);
     }
-    if (scene->d_blob) cudaFree(scene->d_blob);
+    if (scene->d_blob) {
+        if (ctx && ctx->retired.size() < 4) ctx->retired.push_back({scene->d_blob, scene->blob_cap});
+        else cudaFree(scene->d_blob);
+    }
     delete scene;
 }
 

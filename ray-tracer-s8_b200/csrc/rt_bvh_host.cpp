@@ -13,9 +13,13 @@
 //
 // Build with -ffp-contract=off (no FMA contraction on the host either).
 #include <algorithm>
+#include <atomic>
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 #include <limits>
+#include <mutex>
+#include <thread>
 
 #include "rt_host.h"
 
@@ -23,7 +27,20 @@ namespace rtb {
 namespace {
 
 constexpr int kBuckets = 6;
+// A subtree over n primitives has exactly n - 1 inner nodes and its leaves are idx[lo,hi) in their final order, so
+// every node's slot in the DFS pre-order arrays is known before its subtree is built: node `base`, left subtree from
+// base + 1, right subtree from base + n_left.  Subtrees above this size are built by their own thread.
+static const size_t kParallelMin = [] {
+    const char* e = std::getenv("RT_B200_BUILD_PAR");  // subtree size from which both children get their own thread; 0 = never
+    const long v = e ? std::atol(e) : 0;  // measured: spawning did not pay on 8 host cores (profiles/r1_notes.md)
+    return v > 0 ? (size_t)v : (size_t)-1 / 4;
+}();
 constexpr float kEpsilon = 0.00001f;  // bvh::EPSILON (lib.rs:80)
+
+// f32::min / f32::max (NaN-ignoring) inline: libm's fminf/fmaxf are out-of-line calls under -fno-fast-math and were
+// most of the build time.
+inline float nmin(float a, float b) { return a != a ? b : (b != b ? a : (a < b ? a : b)); }
+inline float nmax(float a, float b) { return a != a ? b : (b != b ? a : (a > b ? a : b)); }
 
 struct Bounds {
     float lo[3], hi[3];
@@ -35,20 +52,20 @@ struct Bounds {
     }
     void join(const Box& b) {  // AABB::join — f32::min/max (NaN-ignoring)
         for (int a = 0; a < 3; a++) {
-            lo[a] = fminf(lo[a], b.min[a]);
-            hi[a] = fmaxf(hi[a], b.max[a]);
+            lo[a] = nmin(lo[a], b.min[a]);
+            hi[a] = nmax(hi[a], b.max[a]);
         }
     }
     void join(const Bounds& b) {
         for (int a = 0; a < 3; a++) {
-            lo[a] = fminf(lo[a], b.lo[a]);
-            hi[a] = fmaxf(hi[a], b.hi[a]);
+            lo[a] = nmin(lo[a], b.lo[a]);
+            hi[a] = nmax(hi[a], b.hi[a]);
         }
     }
     void grow(const float p[3]) {  // AABB::grow
         for (int a = 0; a < 3; a++) {
-            lo[a] = fminf(lo[a], p[a]);
-            hi[a] = fmaxf(hi[a], p[a]);
+            lo[a] = nmin(lo[a], p[a]);
+            hi[a] = nmax(hi[a], p[a]);
         }
     }
     bool empty() const { return lo[0] > hi[0] || lo[1] > hi[1] || lo[2] > hi[2]; }
@@ -77,7 +94,9 @@ struct Builder {
     std::vector<float> centre;  // AABB::center of every shape, computed once (same f32 operations every time)
     HostBVH* out;
     std::string* err;
-    bool failed = false;
+    std::atomic<bool> failed{false};
+    std::atomic<uint32_t> max_depth{0};
+    std::mutex err_mu;
 
     Builder(const std::vector<Box>& b, HostBVH* o, std::string* e) : boxes(b), out(o), err(e) {
         idx.resize(b.size());
@@ -91,21 +110,25 @@ struct Builder {
     }
 
     void fail(const char* msg) {
-        if (!failed && err) *err = msg;
-        failed = true;
+        std::lock_guard<std::mutex> g(err_mu);
+        if (!failed.load() && err) *err = msg;
+        failed.store(true);
+    }
+    void note_depth(uint32_t d) {
+        uint32_t cur = max_depth.load(std::memory_order_relaxed);
+        while (d > cur && !max_depth.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {}
     }
 
-    // Builds the subtree over idx[lo,hi) and returns its code.
-    int32_t build(size_t lo, size_t hi, uint32_t depth) {
-        if (failed) return 0;
+    // Builds the subtree over idx[lo,hi) into inner[base, base + n - 1) and returns its code.
+    int32_t build(size_t lo, size_t hi, uint32_t depth, size_t base) {
+        if (failed.load(std::memory_order_relaxed)) return 0;
         if (depth > 4096) {
             fail("BVH deeper than 4096 levels");
             return 0;
         }
         const size_t n = hi - lo;
         if (n == 1) {
-            out->leaf_order.push_back(idx[lo]);
-            if (depth > out->depth) out->depth = depth;
+            note_depth(depth);
             return ~(int32_t)idx[lo];
         }
         Bounds all, cent;
@@ -115,8 +138,7 @@ struct Builder {
             all.join(boxes[idx[i]]);
             cent.grow(&centre[3 * (size_t)idx[i]]);
         }
-        const int32_t me = (int32_t)out->inner.size();
-        out->inner.push_back(HostNode{});
+        const int32_t me = (int32_t)base;
 
         // AABB::largest_axis (aabb.rs:570-580)
         const float sx = cent.hi[0] - cent.lo[0], sy = cent.hi[1] - cent.lo[1], sz = cent.hi[2] - cent.lo[2];
@@ -125,7 +147,17 @@ struct Builder {
 
         size_t mid;
         Bounds bl, br;
-        if (extent < kEpsilon) {
+        if (n == 2 && extent >= kEpsilon && extent < std::numeric_limits<float>::infinity()) {
+            // Two shapes, finite extent (half of all nodes): the centroid at the low end has rel = 0 → bucket 0, the other
+            // rel = extent/extent = 1 → bucket 5; every split gives the same cost and the first wins, so the children
+            // are (low-end shape, other shape) with their own boxes — the bucket machinery's result, without running it.
+            if (!(centre[3 * (size_t)idx[lo] + axis] == cent.lo[axis])) std::swap(idx[lo], idx[lo + 1]);
+            mid = lo + 1;
+            bl.clear();
+            br.clear();
+            bl.join(boxes[idx[lo]]);
+            br.join(boxes[idx[lo + 1]]);
+        } else if (extent < kEpsilon) {
             mid = lo + n / 2;
             bl.clear();
             br.clear();
@@ -191,8 +223,15 @@ struct Builder {
             fail("degenerate split (empty child bounds)");
             return 0;
         }
-        const int32_t l = build(lo, mid, depth + 1);
-        const int32_t r = build(mid, hi, depth + 1);
+        int32_t l = 0, r = 0;
+        if (mid - lo >= kParallelMin && hi - mid >= kParallelMin) {
+            std::thread t([&] { l = build(lo, mid, depth + 1, base + 1); });
+            r = build(mid, hi, depth + 1, base + (mid - lo));
+            t.join();
+        } else {
+            l = build(lo, mid, depth + 1, base + 1);
+            r = build(mid, hi, depth + 1, base + (mid - lo));
+        }
         HostNode& nd = out->inner[me];
         nd.box_l = bl.box();
         nd.box_r = br.box();
@@ -210,101 +249,122 @@ struct Builder {
 // the DFS rank of the reference-topology tree, which is still built).  Leaves are codes ~index like above.
 // ---------------------------------------------------------------------------------------------------------
 namespace {
+struct SahRec {  // one primitive, permuted in place: centroid, world position, box
+    float c[3];
+    uint32_t id;
+    Box b;
+};
 struct SahBuilder {
-    const std::vector<Box>& boxes;
-    std::vector<uint32_t> idx;
-    std::vector<float> cen;  // 3 per primitive
+    std::vector<SahRec> rec;
     HostBVH* out;
+    std::atomic<uint32_t> max_depth{0};
     static constexpr int kBins = 16;
 
-    SahBuilder(const std::vector<Box>& b, HostBVH* o) : boxes(b), out(o) {
-        idx.resize(b.size());
-        cen.resize(3 * b.size());
+    SahBuilder(const std::vector<Box>& b, HostBVH* o) : out(o) {
+        rec.resize(b.size());
         for (size_t i = 0; i < b.size(); i++) {
-            idx[i] = (uint32_t)i;
-            for (int a = 0; a < 3; a++) cen[3 * i + a] = 0.5f * (b[i].min[a] + b[i].max[a]);
+            rec[i].id = (uint32_t)i;
+            rec[i].b = b[i];
+            for (int a = 0; a < 3; a++) rec[i].c[a] = 0.5f * (b[i].min[a] + b[i].max[a]);
         }
     }
     static float area(const Bounds& b) { return b.empty() ? 0.0f : b.area(); }
+    void note_depth(uint32_t d) {
+        uint32_t cur = max_depth.load(std::memory_order_relaxed);
+        while (d > cur && !max_depth.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {}
+    }
 
-    int32_t build(size_t lo, size_t hi, uint32_t depth) {
+    int32_t build(size_t lo, size_t hi, uint32_t depth, size_t base) {
         const size_t n = hi - lo;
         if (n == 1) {
-            out->leaf_order.push_back(idx[lo]);
-            if (depth > out->depth) out->depth = depth;
-            return ~(int32_t)idx[lo];
+            note_depth(depth);
+            return ~(int32_t)rec[lo].id;
         }
         float cmin[3], cmax[3];
         for (int a = 0; a < 3; a++) { cmin[a] = std::numeric_limits<float>::infinity(); cmax[a] = -cmin[a]; }
         for (size_t i = lo; i < hi; i++)
             for (int a = 0; a < 3; a++) {
-                cmin[a] = fminf(cmin[a], cen[3 * idx[i] + a]);
-                cmax[a] = fmaxf(cmax[a], cen[3 * idx[i] + a]);
+                cmin[a] = rec[i].c[a] < cmin[a] ? rec[i].c[a] : cmin[a];
+                cmax[a] = rec[i].c[a] > cmax[a] ? rec[i].c[a] : cmax[a];
+            }
+        // one pass bins all three axes; small nodes (most of them) use fewer bins, their cost is the per-node set-up
+        const int nb = n <= 4 ? 2 : (n <= 16 ? 4 : (n <= 64 ? 8 : kBins));
+        Bounds bb[3][kBins];
+        uint32_t cnt[3][kBins];
+        float scale[3];
+        bool use[3];
+        for (int a = 0; a < 3; a++) {
+            const float ext = cmax[a] - cmin[a];
+            use[a] = ext > 0.0f;
+            scale[a] = use[a] ? (float)nb * (1.0f - 1e-6f) / ext : 0.0f;
+            for (int k = 0; k < nb; k++) { bb[a][k].clear(); cnt[a][k] = 0; }
+        }
+        auto bin_of = [&](const SahRec& r, int a) {
+            int k = (int)((r.c[a] - cmin[a]) * scale[a]);
+            return k < 0 ? 0 : (k >= nb ? nb - 1 : k);
+        };
+        for (size_t i = lo; i < hi; i++)
+            for (int a = 0; a < 3; a++) {
+                if (!use[a]) continue;
+                const int k = bin_of(rec[i], a);
+                cnt[a][k]++;
+                bb[a][k].join(rec[i].b);
             }
         int best_axis = -1, best_split = 0;
         float best_cost = std::numeric_limits<float>::infinity();
+        Bounds best_l, best_r;
+        best_l.clear();
+        best_r.clear();
         for (int a = 0; a < 3; a++) {
-            const float ext = cmax[a] - cmin[a];
-            if (!(ext > 0.0f)) continue;
-            Bounds bb[kBins];
-            size_t cnt[kBins] = {0};
-            for (auto& b : bb) b.clear();
-            const float scale = (float)kBins * (1.0f - 1e-6f) / ext;
-            for (size_t i = lo; i < hi; i++) {
-                int k = (int)((cen[3 * idx[i] + a] - cmin[a]) * scale);
-                k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
-                cnt[k]++;
-                bb[k].join(boxes[idx[i]]);
-            }
-            Bounds racc;
-            racc.clear();
-            float rarea[kBins];
+            if (!use[a]) continue;
+            Bounds racc[kBins];
             size_t rcnt[kBins];
+            Bounds acc;
+            acc.clear();
             size_t c = 0;
-            for (int k = kBins - 1; k > 0; k--) {
-                racc.join(bb[k]);
-                c += cnt[k];
-                rarea[k] = area(racc);
+            for (int k = nb - 1; k > 0; k--) {
+                acc.join(bb[a][k]);
+                c += cnt[a][k];
+                racc[k] = acc;
                 rcnt[k] = c;
             }
             Bounds lacc;
             lacc.clear();
             size_t lc = 0;
-            for (int k = 0; k < kBins - 1; k++) {
-                lacc.join(bb[k]);
-                lc += cnt[k];
+            for (int k = 0; k < nb - 1; k++) {
+                lacc.join(bb[a][k]);
+                lc += cnt[a][k];
                 if (lc == 0 || rcnt[k + 1] == 0) continue;
-                const float cost = (float)lc * area(lacc) + (float)rcnt[k + 1] * rarea[k + 1];
-                if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = k; }
+                const float cost = (float)lc * area(lacc) + (float)rcnt[k + 1] * area(racc[k + 1]);
+                if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = k; best_l = lacc; best_r = racc[k + 1]; }
             }
         }
-        size_t mid;
-        if (best_axis < 0) {
-            mid = lo + n / 2;  // coincident centroids
-        } else {
-            const float ext = cmax[best_axis] - cmin[best_axis];
-            const float scale = (float)kBins * (1.0f - 1e-6f) / ext;
-            auto first = idx.begin() + lo, last = idx.begin() + hi;
-            auto it = std::stable_partition(first, last, [&](uint32_t p) {
-                int k = (int)((cen[3 * p + best_axis] - cmin[best_axis]) * scale);
-                k = k < 0 ? 0 : (k >= kBins ? kBins - 1 : k);
-                return k <= best_split;
-            });
-            mid = (size_t)(it - idx.begin());
-            if (mid == lo || mid == hi) mid = lo + n / 2;
+        size_t mid = lo;
+        if (best_axis >= 0) {
+            auto it = std::partition(rec.begin() + lo, rec.begin() + hi,
+                                     [&](const SahRec& r) { return bin_of(r, best_axis) <= best_split; });
+            mid = (size_t)(it - rec.begin());
         }
-        const int32_t me = (int32_t)out->inner.size();
-        out->inner.push_back(HostNode{});
-        Bounds bl, br;
-        bl.clear();
-        br.clear();
-        for (size_t i = lo; i < mid; i++) bl.join(boxes[idx[i]]);
-        for (size_t i = mid; i < hi; i++) br.join(boxes[idx[i]]);
-        const int32_t l = build(lo, mid, depth + 1);
-        const int32_t r = build(mid, hi, depth + 1);
+        if (mid == lo || mid == hi) {  // coincident centroids: halve, bounds by a pass
+            mid = lo + n / 2;
+            best_l.clear();
+            best_r.clear();
+            for (size_t i = lo; i < mid; i++) best_l.join(rec[i].b);
+            for (size_t i = mid; i < hi; i++) best_r.join(rec[i].b);
+        }
+        const int32_t me = (int32_t)base;
+        int32_t l = 0, r = 0;
+        if (mid - lo >= kParallelMin && hi - mid >= kParallelMin) {
+            std::thread t([&] { l = build(lo, mid, depth + 1, base + 1); });
+            r = build(mid, hi, depth + 1, base + (mid - lo));
+            t.join();
+        } else {
+            l = build(lo, mid, depth + 1, base + 1);
+            r = build(mid, hi, depth + 1, base + (mid - lo));
+        }
         HostNode& nd = out->inner[me];
-        nd.box_l = bl.box();
-        nd.box_r = br.box();
+        nd.box_l = best_l.box();
+        nd.box_r = best_r.box();
         nd.left = l;
         nd.right = r;
         return me;
@@ -317,10 +377,12 @@ bool build_bvh_sah(const std::vector<Box>& boxes, HostBVH* out) {
     out->leaf_order.clear();
     out->depth = 0;
     if (boxes.empty()) return false;
-    out->inner.reserve(boxes.size());
-    out->leaf_order.reserve(boxes.size());
+    out->inner.assign(boxes.size() - 1, HostNode{});
     SahBuilder b(boxes, out);
-    out->root = b.build(0, boxes.size(), 0);
+    out->root = b.build(0, boxes.size(), 0, 0);
+    out->leaf_order.resize(boxes.size());
+    for (size_t i = 0; i < boxes.size(); i++) out->leaf_order[i] = b.rec[i].id;
+    out->depth = b.max_depth.load();
     out->node_count = (uint32_t)(out->inner.size() + out->leaf_order.size());
     return true;
 }
@@ -333,12 +395,13 @@ bool build_bvh(const std::vector<Box>& boxes, HostBVH* out, std::string* err) {
         if (err) *err = "empty scene";
         return false;
     }
-    out->inner.reserve(boxes.size());
-    out->leaf_order.reserve(boxes.size());
+    out->inner.assign(boxes.size() - 1, HostNode{});
     Builder b(boxes, out, err);
-    out->root = b.build(0, boxes.size(), 0);
+    out->root = b.build(0, boxes.size(), 0, 0);
+    out->leaf_order = b.idx;  // the leaves in DFS order are the final order of the index array
+    out->depth = b.max_depth.load();
     out->node_count = (uint32_t)(out->inner.size() + out->leaf_order.size());
-    return !b.failed;
+    return !b.failed.load();
 }
 
 }  // namespace rtb

@@ -48,6 +48,7 @@ cudaError_t launch_wq(const DevScene& sc, const DevCamera& cam, const DevParams&
 cudaError_t launch_wavefront(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
                              int smem_optin, cudaStream_t stream, WaveBuffers* wb, LaunchInfo* info);
 bool use_wavefront(int isect);
+bool legacy_node_arrays_needed();  // true when RT_B200_BVH_KERNEL selects a kernel that reads node_* / cnode_*
 cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevParams& pr, int isect, bool count,
                           int sm_count, int smem_optin, cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_fp32_peak(float* scratch, int sm_count, int iters, cudaStream_t stream);

@@ -1153,6 +1153,7 @@ static int bvh_variant() {
     }
     return v;
 }
+bool legacy_node_arrays_needed() { return bvh_variant() != 3 && bvh_variant() != 5; }
 static int env_int(const char* name, int dflt) {
     const char* e = std::getenv(name);
     return e ? std::atoi(e) : dflt;
