@@ -339,7 +339,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     const size_t o_nd = take(nl * 8), o_mat = take((size_t)n * 16), o_em = take((size_t)n * 4);
     const size_t o_rank = take((size_t)n * 4), o_box = take((size_t)n * 32);
     const size_t o_ca = take(nl * 16), o_cb = take(nl * 16), o_cc = take(nl * 16);
-    const size_t o_la = take((size_t)ni * 16), o_lb = take((size_t)ni * 16), o_lc = take((size_t)ni * 16);
+    const size_t o_la = take((size_t)ni * 48);  // lnode_abc: three float4 per node, one 48-byte record
     const size_t o_ld = take((size_t)ni * 8);
     // brute-force kernel: spheres in pairs for the packed f32x2 filter, padded to a multiple of 8 spheres
     const uint32_t ns8 = (n_spheres + 7u) & ~7u;
@@ -550,8 +550,6 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             sub[i] = Sub{a.n_s + b.n_s, a.n_t + b.n_t, a.n_s ? a.first_s : b.first_s, a.n_t ? a.first_t : b.first_t};
         }
         float* la = (float*)(blob.data() + o_la);
-        float* lb = (float*)(blob.data() + o_lb);
-        float* lc = (float*)(blob.data() + o_lc);
         int32_t* ld = (int32_t*)(blob.data() + o_ld);
         auto leaf_code = [](uint32_t first, uint32_t count) { return ~(int32_t)((first << 5) | (count - 1)); };
         struct Item { int32_t code; uint32_t parent; int side; };
@@ -580,9 +578,9 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
                 float lcn[3], lhh[3], rcn[3], rhh[3];
                 centre_half_of(hn.box_l, lcn, lhh);
                 centre_half_of(hn.box_r, rcn, rhh);
-                float* pa = la + 4 * (size_t)me;
-                float* pb = lb + 4 * (size_t)me;
-                float* pc = lc + 4 * (size_t)me;
+                float* pa = la + 12 * (size_t)me;
+                float* pb = pa + 4;
+                float* pc = pa + 8;
                 pa[0] = lcn[0]; pa[1] = lcn[1]; pa[2] = lcn[2]; pa[3] = lhh[0];
                 pb[0] = lhh[1]; pb[1] = lhh[2]; pb[2] = rcn[0]; pb[3] = rcn[1];
                 pc[0] = rcn[2]; pc[1] = rhh[0]; pc[2] = rhh[1]; pc[3] = rhh[2];
@@ -653,8 +651,6 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     d.cnode_b = (const float4*)(sc->d_blob + o_cb);
     d.cnode_c = (const float4*)(sc->d_blob + o_cc);
     d.lnode_a = (const float4*)(sc->d_blob + o_la);
-    d.lnode_b = (const float4*)(sc->d_blob + o_lb);
-    d.lnode_c = (const float4*)(sc->d_blob + o_lc);
     d.lnode_d = (const int2*)(sc->d_blob + o_ld);
     d.lni = lni;
     d.lroot = lroot;

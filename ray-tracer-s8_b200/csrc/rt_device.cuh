@@ -40,9 +40,7 @@ struct DevScene {
     const float4* cnode_c;
     // the same tree with every subtree of <= L same-kind primitives collapsed into one leaf (lanes kernel):
     // pids are in DFS order, so a subtree is a contiguous pid range; leaf code = ~((first_pid << 5) | (count-1))
-    const float4* lnode_a;
-    const float4* lnode_b;
-    const float4* lnode_c;
+    const float4* lnode_a;  // [lni*3] one 48-byte record per node (a | b | c): a single address per visit
     const int2* lnode_d;
     uint32_t lni;          // inner nodes of the collapsed tree
     int lroot;             // its root code

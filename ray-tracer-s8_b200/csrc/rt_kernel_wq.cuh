@@ -104,22 +104,20 @@ __global__ void __launch_bounds__(NW * 32, 1) render_kernel_wq(const DevScene sc
         float4* p = smem_dyn;
         float4* s_sph = p;  p += sc.ns;
         float4* s_tri = p;  p += 4 * sc.nt;
-        float4* s_na = p;   p += sc.lni;
-        float4* s_nb = p;   p += sc.lni;
-        float4* s_nc = p;   p += sc.lni;
+        float4* s_na = p;   p += 3 * sc.lni;  // 48-byte node records
         int2* s_nd = reinterpret_cast<int2*>(p);
         for (uint32_t i = threadIdx.x; i < sc.ns; i += NT) s_sph[i] = __ldg(&sc.sph[i]);
         for (uint32_t i = threadIdx.x; i < 4 * sc.nt; i += NT) s_tri[i] = __ldg(&sc.tri[i]);
         for (uint32_t i = threadIdx.x; i < sc.lni; i += NT) {
-            s_na[i] = __ldg(&sc.lnode_a[i]);
-            s_nb[i] = __ldg(&sc.lnode_b[i]);
-            s_nc[i] = __ldg(&sc.lnode_c[i]);
+            s_na[3 * i] = __ldg(&sc.lnode_a[3 * i]);
+            s_na[3 * i + 1] = __ldg(&sc.lnode_a[3 * i + 1]);
+            s_na[3 * i + 2] = __ldg(&sc.lnode_a[3 * i + 2]);
             s_nd[i] = __ldg(&sc.lnode_d[i]);
         }
         __syncthreads();
-        sv.sph = s_sph; sv.tri = s_tri; sv.na = s_na; sv.nb = s_nb; sv.nc = s_nc; sv.nd = s_nd;
+        sv.sph = s_sph; sv.tri = s_tri; sv.na = s_na; sv.nb = nullptr; sv.nc = nullptr; sv.nd = s_nd;
     } else {
-        sv.sph = sc.sph; sv.tri = sc.tri; sv.na = sc.lnode_a; sv.nb = sc.lnode_b; sv.nc = sc.lnode_c; sv.nd = sc.lnode_d;
+        sv.sph = sc.sph; sv.tri = sc.tri; sv.na = sc.lnode_a; sv.nb = nullptr; sv.nc = nullptr; sv.nd = sc.lnode_d;
     }
 
     const unsigned FULL = 0xffffffffu;
@@ -383,7 +381,8 @@ __global__ void __launch_bounds__(NW * 32, 1) render_kernel_wq(const DevScene sc
                 while (__ballot_sync(FULL, cur >= 0) != 0 && k < wa.node_burst) {
                     k++;
                     if (cur >= 0) {
-                        const float4 a = sv.na[cur], b = sv.nb[cur], c = sv.nc[cur];
+                        const float4* nrec = sv.na + 3 * cur;
+                        const float4 a = nrec[0], b = nrec[1], c = nrec[2];
                         const int2 ch = sv.nd[cur];
                         const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
                         const float rcx = fmaf(b.z, ix, qx), rcy = fmaf(b.w, iy, qy), rcz = fmaf(c.x, iz, qz);

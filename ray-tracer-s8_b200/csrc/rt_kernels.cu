@@ -678,6 +678,7 @@ __global__ void __launch_bounds__(THREADS) render_kernel(const DevScene sc, cons
 // 10 FMNMX: the first form saturated the ALU pipe at 75 % with the FMA pipe at 23 %), FMA pre-filter in
 // front of the exact triangle test.  Same while-while structure, same results.
 // ---------------------------------------------------------------------------------------------
+constexpr int TR_DONE = (int)0x80000000;  // traversal finished (never a leaf code: first_pid < 2^26)
 template <bool COUNT>
 __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
     best.pid = -1;
@@ -713,7 +714,8 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
     if (!sc.ltree) return;
     for (;;) {
         while (cur >= 0) {
-            const float4 a = sv.na[cur], b = sv.nb[cur], c = sv.nc[cur];
+            const float4* nrec = sv.na + 3 * cur;
+            const float4 a = nrec[0], b = nrec[1], c = nrec[2];
             const int2 ch = sv.nd[cur];
             // left box: c = (a.x,a.y,a.z) h = (a.w,b.x,b.y); right: c = (b.z,b.w,c.x) h = (c.y,c.z,c.w)
             const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
@@ -725,19 +727,17 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
             const bool hl = tl <= fl + slack;
             const bool hr = tr <= fr + slack;
             if (COUNT) ctr.v[CTR_SLAB] += 2;
-            if (hl && hr) {
-                const bool swap = tr < tl;
-                stack[sp++] = swap ? ch.x : ch.y;
-                cur = swap ? ch.y : ch.x;
-            } else if (hl) {
-                cur = ch.x;
-            } else if (hr) {
-                cur = ch.y;
-            } else {
-                if (sp == 0) return;
-                cur = stack[--sp];
+            // branch-light step: push and pop are short predicated blocks, the loop has one exit
+            const bool swap = tr < tl;
+            if (hl && hr) stack[sp++] = swap ? ch.x : ch.y;
+            int nxt = (hr && (!hl || swap)) ? ch.y : ch.x;  // the nearer (or the only) child
+            if (!(hl || hr)) {
+                nxt = TR_DONE;
+                if (sp != 0) nxt = stack[--sp];
             }
+            cur = nxt;
         }
+        if (cur == TR_DONE) return;
         // leaf = contiguous pid range of one kind: code = ~((first << 5) | (count - 1))
         const int first = (~cur) >> 5, count = ((~cur) & 31) + 1;
         if (first < ns) {
@@ -901,25 +901,23 @@ __global__ void __launch_bounds__(THREADS, MINB) render_kernel_lanes(const DevSc
             for (uint32_t i = threadIdx.x; i < ns8; i += THREADS) s_sph2[i] = __ldg(&sc.sph2[i]);
         }
         sv.sph2 = s_sph2;
-        float4* s_na = p;   p += sc.ni;
-        float4* s_nb = p;   p += sc.ni;
-        float4* s_nc = p;   p += sc.ni;
+        float4* s_na = p;   p += 3 * sc.ni;  // 48-byte node records
         int2* s_nd = reinterpret_cast<int2*>(p);
         for (uint32_t i = threadIdx.x; i < sc.ns; i += THREADS) s_sph[i] = __ldg(&sc.sph[i]);
         for (uint32_t i = threadIdx.x; i < 4 * sc.nt; i += THREADS) s_tri[i] = __ldg(&sc.tri[i]);
         if (ISECT == RT_INTERSECT_BVH) {
             for (uint32_t i = threadIdx.x; i < sc.lni; i += THREADS) {
-                s_na[i] = __ldg(&sc.lnode_a[i]);
-                s_nb[i] = __ldg(&sc.lnode_b[i]);
-                s_nc[i] = __ldg(&sc.lnode_c[i]);
+                s_na[3 * i] = __ldg(&sc.lnode_a[3 * i]);
+                s_na[3 * i + 1] = __ldg(&sc.lnode_a[3 * i + 1]);
+                s_na[3 * i + 2] = __ldg(&sc.lnode_a[3 * i + 2]);
                 s_nd[i] = __ldg(&sc.lnode_d[i]);
             }
         }
         __syncthreads();
-        sv.sph = s_sph; sv.tri = s_tri; sv.na = s_na; sv.nb = s_nb; sv.nc = s_nc; sv.nd = s_nd;
+        sv.sph = s_sph; sv.tri = s_tri; sv.na = s_na; sv.nb = nullptr; sv.nc = nullptr; sv.nd = s_nd;
     } else {
         sv.sph2 = sc.sph2;
-        sv.sph = sc.sph; sv.tri = sc.tri; sv.na = sc.lnode_a; sv.nb = sc.lnode_b; sv.nc = sc.lnode_c; sv.nd = sc.lnode_d;
+        sv.sph = sc.sph; sv.tri = sc.tri; sv.na = sc.lnode_a; sv.nb = nullptr; sv.nc = nullptr; sv.nd = sc.lnode_d;
     }
 
     const unsigned FULL = 0xffffffffu;
