@@ -30,6 +30,7 @@ struct rt_ctx {
     float* d_scratch = nullptr;
     WaveBuffers wave;
     WqBuffers wq;
+    DeviceBuild dbuild;
     // scene upload: one pinned staging buffer the blob is assembled in, and a few retired device blobs kept for the
     // next rt_scene_create (a slave makes one scene per job: cudaMalloc/cudaFree per job were a third of a small job)
     uint8_t* h_stage = nullptr;
@@ -44,6 +45,7 @@ struct rt_scene {
     size_t blob_bytes = 0, blob_cap = 0;
     DevScene dev{};
     uint32_t n = 0, n_nodes = 0, depth = 0;
+    uint32_t device_tree_depth = 0;  // > 0: the traversal tree was built on the device (LBVH), this deep
     std::vector<uint32_t> rank_by_world;  // world position → DFS leaf rank
 };
 
@@ -136,6 +138,7 @@ void rt_shutdown(rt_ctx* ctx) {
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     free_wave_buffers(&ctx->wave);
     free_wq_buffers(&ctx->wq);
+    free_device_build(&ctx->dbuild);
     for (auto& r : ctx->retired) cudaFree(r.p);
     ctx->retired.clear();
     if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
@@ -360,6 +363,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         ctx->h_stage_bytes = cap;
     }
     blob.p = ctx->h_stage;
+    lap("staging buffer");
     memset(blob.p, 0, blob.n);
     float* h_sph = (float*)(blob.data() + o_sph);
     float* h_tri = (float*)(blob.data() + o_tri);
@@ -472,6 +476,17 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     int32_t lroot = 0;
     std::vector<uint32_t> big_world;  // split layout: world positions of the primitives kept out of the tree
     bool ltree = true;
+    // RT_B200_BUILD = auto (default) | host | device.  device: the traversal tree is an LBVH built on the GPU after the
+    // upload (rt_bvh_device.cu) instead of the host's binned-SAH tree; auto picks it from kDeviceBuildMin primitives,
+    // where the host build costs more than the LBVH's extra slab tests (profiles/r1_notes.md).
+    static const int build_mode = [] {
+        const char* e = std::getenv("RT_B200_BUILD");
+        return (e && std::strcmp(e, "host") == 0) ? 0 : ((e && std::strcmp(e, "device") == 0) ? 2 : 1);
+    }();
+    constexpr uint32_t kDeviceBuildMin = 8192;
+    bool device_tree = false;
+    std::vector<float> dev_boxes;     // boxes and pids of the primitives the device-built tree covers
+    std::vector<uint32_t> dev_pid;
     {
         // RT_B200_TREE = split (default) | sah | ref.  ref: the reference-topology tree itself.  sah: a 3-axis binned-SAH
         // tree over all primitives.  split: the primitives whose box area is a large share of the whole scene's go to a
@@ -516,6 +531,17 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
                 }
             if (rest.empty()) {
                 ltree = false;
+            } else if (rest.size() >= 2 && (build_mode == 2 || (build_mode == 1 && rest.size() >= kDeviceBuildMin))) {
+                device_tree = true;
+                dev_boxes.resize(6 * rest.size());
+                dev_pid.resize(rest.size());
+                for (size_t i = 0; i < rest.size(); i++) {
+                    for (int a = 0; a < 3; a++) {
+                        dev_boxes[6 * i + a] = rest[i].min[a];
+                        dev_boxes[6 * i + 3 + a] = rest[i].max[a];
+                    }
+                    dev_pid[i] = pid_of_world[rest_world[i]];
+                }
             } else {
                 use_sah = build_bvh_sah(rest, &sah) && sah.depth <= (uint32_t)MAX_STACK;
                 if (use_sah) {  // leaf codes: subset index → world position
@@ -565,7 +591,12 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             return 0;
         };
         bool root_leaf = true;
-        if (ltree) lroot = classify(T.root, &root_leaf);
+        if (device_tree) {  // nodes 0 .. n-2 are written on the device after the upload; the root is node 0
+            lni = (uint32_t)dev_pid.size() - 1;
+            lroot = 0;
+        } else if (ltree) {
+            lroot = classify(T.root, &root_leaf);
+        }
         if (!root_leaf) {
             todo.push_back(Item{T.root, 0, -1});
             while (!todo.empty()) {
@@ -639,6 +670,19 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         return set_err(ctx, RT_ERR_CUDA, "scene upload failed: %s", cudaGetErrorString(e));
     }
     lap("upload");
+    if (device_tree) {
+        uint32_t depth = 0;
+        e = build_lbvh_device(&ctx->dbuild, dev_boxes.data(), dev_pid.data(), (uint32_t)dev_pid.size(),
+                              (float4*)(sc->d_blob + o_la), (int2*)(sc->d_blob + o_ld), &depth, ctx->stream);
+        if (e != cudaSuccess || depth > (uint32_t)MAX_STACK) {
+            ctx->retired.push_back({sc->d_blob, sc->blob_cap});
+            delete sc;
+            if (e != cudaSuccess) return set_err(ctx, RT_ERR_CUDA, "device BVH build failed: %s", cudaGetErrorString(e));
+            return set_err(ctx, RT_ERR_UNSUPPORTED, "device-built tree depth %u exceeds the traversal stack (%d)", depth, MAX_STACK);
+        }
+        sc->device_tree_depth = depth;
+        lap("device tree build");
+    }
     DevScene& d = sc->dev;
     d.sph = (const float4*)(sc->d_blob + o_sph);
     d.tri = (const float4*)(sc->d_blob + o_tri);

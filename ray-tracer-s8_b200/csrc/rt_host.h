@@ -44,6 +44,15 @@ bool use_wq(int isect, const DevParams& pr);
 cudaError_t launch_wq(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
                       int smem_optin, cudaStream_t stream, WqBuffers* wb, LaunchInfo* info);
 
+// rt_bvh_device.cu: LBVH + refit of the traversal tree on the device (scratch owned by the context)
+struct DeviceBuild {
+    void* mem = nullptr;
+    size_t bytes = 0;
+};
+void free_device_build(DeviceBuild* b);
+cudaError_t build_lbvh_device(DeviceBuild* buf, const float* h_boxes, const uint32_t* h_pid_of, uint32_t n,
+                              float4* lnode_abc, int2* lnode_d, uint32_t* depth_out, cudaStream_t stream);
+
 // rt_kernels.cu
 cudaError_t launch_wavefront(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
                              int smem_optin, cudaStream_t stream, WaveBuffers* wb, LaunchInfo* info);

@@ -156,6 +156,38 @@ def test_kernel_variants_agree(rt, O):
     assert hashlib.sha256(ref.tobytes()).hexdigest() == digests["lanes"]
 
 
+def test_device_built_tree_agrees(rt, O):
+    """the traversal tree built on the GPU (Morton LBVH + refit, RT_B200_BUILD=device) culls
+    conservatively like the host's SAH tree, so the frame is the same bytes — spheres + plane (split layout) and a
+    scene large enough for the automatic switch (>= 8192 primitives)."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, hashlib; sys.path.insert(0, 'ray-tracer-s8_b200'); import rt_b200 as rt; from rt_b200 import scenes;"
+        "ctx = rt.Context(0); out = [];\n"
+        "for n, plane in ((300, True), (9000, False)):\n"
+        "    sc = ctx.scene(scenes.synthetic_spheres(n, 5), scenes.ground_plane() if plane else None)\n"
+        "    img = ctx.render_frame(sc, rt.make_params(160, 96, spp=2, max_bounces=5, seed=4, intersector=2))\n"
+        "    out.append(hashlib.sha256(img.tobytes()).hexdigest()); sc.close()\n"
+        "print(' '.join(out))"
+    )
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    digests = {}
+    for mode in ("host", "device", "auto"):
+        env = dict(os.environ, RT_B200_BUILD=mode)
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+        assert out.returncode == 0, (mode, out.stderr[-500:])
+        digests[mode] = out.stdout.strip().splitlines()[-1]
+    assert len(set(digests.values())) == 1, digests
+    ref, _ = O.render_frame(rt.scenes.synthetic_spheres(300, 5), rt.scenes.ground_plane(), 160, 96, 2, 5, seed=4)
+    assert hashlib.sha256(ref.tobytes()).hexdigest() == digests["device"].split()[0]
+    ref2, _ = O.render_frame(rt.scenes.synthetic_spheres(9000, 5), None, 160, 96, 2, 5, seed=4)
+    assert hashlib.sha256(ref2.tobytes()).hexdigest() == digests["device"].split()[1]
+
+
 def test_camera_parameters_and_seeds(ctx, rt, O):
     sp, tr = rt.scenes.synthetic_spheres(64, 2), rt.scenes.ground_plane()
     cam = dict(cam_origin=(0.5, 0.25, 1.0), aperture=0.02, focus_distance=6.0, field_of_view=1.0, focal_length=1.5)
