@@ -45,6 +45,8 @@ struct WqArgs {
     uint32_t node_burst;   // slab steps between two votes
     uint32_t t_leaf, t_pend, t_fin;  // a waiting state is served when this many lanes (or more lanes than at nodes) are in it
     uint32_t scene_bytes;  // shared-memory offset of the per-warp areas
+    uint32_t cta_phases;   // 1: LOGIC and TRACE are CTA-wide phases separated by barriers
+    uint32_t trace_budget; // CTA-wide phases: a warp leaves TRACE after this many votes (0 = no bound)
 };
 
 __host__ __device__ inline size_t wq_state_bytes(size_t n, uint32_t depth) { return n * (16 * 4 + 4 + 4 + 4 * (size_t)depth); }
@@ -368,7 +370,15 @@ __global__ void __launch_bounds__(NW * 32, 1) render_kernel_wq(const DevScene sc
         n_end = 0;
         __syncwarp();
 
-        if (qn == 0 && __ballot_sync(FULL, chain >= 0) == 0) break;  // every chain of this warp is retired
+        const bool warp_done = qn == 0 && __ballot_sync(FULL, chain >= 0) == 0;  // every chain of this warp is retired
+        if (wa.cta_phases) {
+            // CTA-wide phases: all warps run LOGIC together, then TRACE together, so each phase's code is what the SM's
+            // instruction caches hold; a finished warp keeps meeting the barriers until the whole CTA is done
+            if (__syncthreads_and(warp_done)) break;
+        } else if (warp_done) {
+            break;
+        }
+        uint32_t trips = 0;
 
         // =====================================================================================
         // TRACE: slab steps for the lanes at inner nodes; the other states are served when enough lanes wait in them
@@ -418,6 +428,7 @@ __global__ void __launch_bounds__(NW * 32, 1) render_kernel_wq(const DevScene sc
                 if (lane == 0) ctr.v[CTR_TOTAL_LANES] += 32;
             }
             if ((nm | lm | pm | fm) == 0) break;  // nothing in flight, nothing queued
+            if (wa.trace_budget && ++trips > wa.trace_budget) break;  // CTA-wide phases: bound the wait at the barrier
 
             if (n_leaf != 0 && (n_leaf >= wa.t_leaf || n_leaf >= n_node)) {
                 // ---- FILTER step on the first primitive of the leaf: code = ~((first << 5) | (count - 1)) ----
@@ -511,6 +522,7 @@ __global__ void __launch_bounds__(NW * 32, 1) render_kernel_wq(const DevScene sc
             }
         }
         __syncwarp();
+        if (wa.cta_phases) __syncthreads();
     }
 
     ctr.v[CTR_RAYS] = rays;

@@ -1413,6 +1413,13 @@ cudaError_t launch_wq(const DevScene& sc, const DevCamera& cam, const DevParams&
         ww[3] = env_int("RT_B200_WQ_T_FIN", 6);
     }
     wa.node_burst = ww[0]; wa.t_leaf = ww[1]; wa.t_pend = ww[2]; wa.t_fin = ww[3];
+    static int cta_phases = -1, trace_budget = 0;
+    if (cta_phases < 0) {
+        cta_phases = env_int("RT_B200_WQ_SYNC", 0);
+        trace_budget = env_int("RT_B200_WQ_BUDGET", 0);
+    }
+    wa.cta_phases = (uint32_t)cta_phases;
+    wa.trace_budget = (uint32_t)trace_budget;
     wa.scene_bytes = (uint32_t)scene_bytes;
     fn<<<(unsigned)grid, nw * 32, dyn, stream>>>(sc, cam, prm, wa);
     if (info) {
