@@ -334,14 +334,32 @@ __device__ __forceinline__ float brute_margin(const float4 s, V3 o, V3 d) {
     return fmaf(bh, bh, fmaf(oc2, -0.99998f, s.w));
 }
 
-// a group of 8 spheres in which at least one passed the filter: re-test each, run the slow path for those
+// a group of 8 spheres (first is a multiple of 8) in which at least one passed the filter: the four pairs once more
+// in packed arithmetic, this time keeping WHICH spheres passed, then the slow path for exactly those
 template <bool COUNT>
-__device__ __noinline__ void brute_group_slow(const DevScene& sc, const float4* sph, int first, int count, V3 o, V3 d,
-                                              Hit& best, Ctr& ctr) {
-#pragma unroll 1
-    for (int k = 0; k < count; k++) {
-        const float4 s = sph[first + k];
-        if (!(brute_margin(s, o, d) < 0.0f)) brute_sphere_slow<COUNT>(sc, s, first + k, o, d, best, ctr);
+__device__ __noinline__ void brute_group_slow(const DevScene& sc, const float4* sph, const float4* sph2, int first, int count,
+                                              V3 o, V3 d, bool all, Hit& best, Ctr& ctr) {
+    const f32x2 ox2 = pk2(o.x, o.x), oy2 = pk2(o.y, o.y), oz2 = pk2(o.z, o.z);
+    const f32x2 dx2 = pk2(d.x, d.x), dy2 = pk2(d.y, d.y), dz2 = pk2(d.z, d.z);
+    const f32x2 kk2 = pk2(-0.99998f, -0.99998f);
+    unsigned mask = 0;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const float4 A = sph2[2 * ((first >> 1) + k)], B = sph2[2 * ((first >> 1) + k) + 1];
+        const f32x2 ocx = add2(ox2, pk2(A.x, A.y)), ocy = add2(oy2, pk2(A.z, A.w)), ocz = add2(oz2, pk2(B.x, B.y));
+        const f32x2 bh = fma2(ocz, dz2, fma2(ocy, dy2, mul2(ocx, dx2)));
+        const f32x2 oc2 = fma2(ocz, ocz, fma2(ocy, ocy, mul2(ocx, ocx)));
+        float m_lo, m_hi;
+        upk2(fma2(bh, bh, fma2(oc2, kk2, pk2(B.z, B.w))), m_lo, m_hi);
+        mask |= (!(m_lo < 0.0f) ? 1u : 0u) << (2 * k);
+        mask |= (!(m_hi < 0.0f) ? 1u : 0u) << (2 * k + 1);
+    }
+    if (all) mask = 0xffu;  // a non-finite ray: every sphere goes through the exact arithmetic
+    mask &= (1u << count) - 1u;
+    while (mask) {
+        const int k = __ffs(mask) - 1;
+        mask &= mask - 1u;
+        brute_sphere_slow<COUNT>(sc, sph[first + k], first + k, o, d, best, ctr);
     }
 }
 
@@ -380,8 +398,8 @@ __device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView&
         }
         if (COUNT) ctr.v[CTR_SPH_TEST] += min(16, ns - i);
         if (!(fmaxf(m0, m1) < 0.0f) || weird) {
-            if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, i, min(8, ns - i), o, d, best, ctr);
-            if ((!(m1 < 0.0f) || weird) && i + 8 < ns) brute_group_slow<COUNT>(sc, sv.sph, i + 8, min(8, ns - i - 8), o, d, best, ctr);
+            if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, sv.sph2, i, min(8, ns - i), o, d, weird, best, ctr);
+            if ((!(m1 < 0.0f) || weird) && i + 8 < ns) brute_group_slow<COUNT>(sc, sv.sph, sv.sph2, i + 8, min(8, ns - i - 8), o, d, weird, best, ctr);
         }
     }
     if (i < ns8) {
@@ -389,7 +407,7 @@ __device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView&
 #pragma unroll
         for (int k = 0; k < 4; k++) m0 = pair_margin((i >> 1) + k, m0);
         if (COUNT) ctr.v[CTR_SPH_TEST] += ns - i;
-        if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, i, ns - i, o, d, best, ctr);
+        if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, sv.sph2, i, ns - i, o, d, weird, best, ctr);
     }
     const int nt = (int)sc.nt;
     for (int j = 0; j < nt; j++) test_triangle<COUNT>(sc, sv.tri, j, ns + j, o, d, best, ctr);
