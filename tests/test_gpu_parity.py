@@ -87,6 +87,8 @@ def test_c3_scene_crop(ctx, rt, O):
     dict(n=300, plane=True, w=7, h=5, spp=5, mb=6),          # frame smaller than one tile
     dict(n=150, plane=False, w=256, h=8, spp=1, mb=12),
     dict(n=96, plane=True, w=64, h=64, spp=2, mb=62),        # deepest path this build supports
+    dict(n=9, plane=False, w=96, h=64, spp=2, mb=5),         # packed sphere pairs: one full group + one sphere
+    dict(n=23, plane=True, w=96, h=64, spp=2, mb=5),         # ... a 16-group whose second half is partial, odd count
 ])
 def test_edge_cases(ctx, rt, O, isect, case):
     sp = rt.scenes.synthetic_spheres(case["n"], 17) if case["n"] else None
