@@ -902,12 +902,12 @@ __device__ __forceinline__ void trace_list(const DevScene& sc, const SceneView& 
 // next pixel of the warp's current 8x4 tile (the warp pulls tiles from the global ticket counter) instead of
 // idling until the slowest pixel of the tile is done; every trip of the loop is one nearest-hit query.
 // ---------------------------------------------------------------------------------------------
-template <int ISECT, bool SMEM, bool COUNT, bool LISTS, int MINB = 3>
-__global__ void __launch_bounds__(THREADS, MINB) render_kernel_lanes(const DevScene sc, const DevCamera cam,
+template <int ISECT, bool SMEM, bool COUNT, bool LISTS, int MINB = 3, int TPB = THREADS>
+__global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene sc, const DevCamera cam,
                                                                 const DevParams pr) {
     extern __shared__ float4 smem_dyn[];
     // per warp: candidate lists of its two most recent tiles (LISTS variant only; measured slower)
-    __shared__ ListEntry s_lists[LISTS ? WARPS : 1][2][LISTS ? LIST_CAP + 2 : 1];
+    __shared__ ListEntry s_lists[LISTS ? TPB / 32 : 1][2][LISTS ? LIST_CAP + 2 : 1];
     SceneView sv;
     if (SMEM) {
         float4* p = smem_dyn;
@@ -916,15 +916,15 @@ __global__ void __launch_bounds__(THREADS, MINB) render_kernel_lanes(const DevSc
         float4* s_sph2 = p;  // brute force only: the pair-packed copy of the spheres
         if (ISECT == RT_INTERSECT_BRUTE) {
             const uint32_t ns8 = (sc.ns + 7u) & ~7u;
-            for (uint32_t i = threadIdx.x; i < ns8; i += THREADS) s_sph2[i] = __ldg(&sc.sph2[i]);
+            for (uint32_t i = threadIdx.x; i < ns8; i += TPB) s_sph2[i] = __ldg(&sc.sph2[i]);
         }
         sv.sph2 = s_sph2;
         float4* s_na = p;   p += 3 * sc.ni;  // 48-byte node records
         int2* s_nd = reinterpret_cast<int2*>(p);
-        for (uint32_t i = threadIdx.x; i < sc.ns; i += THREADS) s_sph[i] = __ldg(&sc.sph[i]);
-        for (uint32_t i = threadIdx.x; i < 4 * sc.nt; i += THREADS) s_tri[i] = __ldg(&sc.tri[i]);
+        for (uint32_t i = threadIdx.x; i < sc.ns; i += TPB) s_sph[i] = __ldg(&sc.sph[i]);
+        for (uint32_t i = threadIdx.x; i < 4 * sc.nt; i += TPB) s_tri[i] = __ldg(&sc.tri[i]);
         if (ISECT == RT_INTERSECT_BVH) {
-            for (uint32_t i = threadIdx.x; i < sc.lni; i += THREADS) {
+            for (uint32_t i = threadIdx.x; i < sc.lni; i += TPB) {
                 s_na[3 * i] = __ldg(&sc.lnode_a[3 * i]);
                 s_na[3 * i + 1] = __ldg(&sc.lnode_a[3 * i + 1]);
                 s_na[3 * i + 2] = __ldg(&sc.lnode_a[3 * i + 2]);
@@ -1188,12 +1188,25 @@ static int list_max_prims() {  // RT_B200_LIST_MAX=N enables the per-tile primar
     if (v < 0) v = env_int("RT_B200_LIST_MAX", 0);
     return v;
 }
+// RT_B200_LANES_TPB = 768 (one CTA per SM, default) | 384 (2) | 256 (3): the same 24 warps per SM; fewer CTAs keep fewer
+// copies of the scene in shared memory and leave more of the 228 KB to L1, where the traversal stacks live
+// (C3: 40.7 ms at 3 x 256, 39.8 at 2 x 384, 39.5 at 1 x 768; profiles/r1_notes.md)
+static int lanes_tpb() {
+    static int v = -1;
+    if (v < 0) {
+        v = env_int("RT_B200_LANES_TPB", 768);
+        if (v != 384 && v != 256) v = 768;
+    }
+    return v;
+}
 template <int ISECT, bool SMEM>
 static KernelFn pick_lanes(bool count) {
     if (ISECT == RT_INTERSECT_BVH && list_max_prims() > 0 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, true>;
     static int minb = -1;  // RT_B200_LANES_MINB=4: 64 registers, 32 resident warps per SM (experiment)
     if (minb < 0) minb = env_int("RT_B200_LANES_MINB", 3);
     if (minb == 4 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 4>;
+    if (lanes_tpb() == 384 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 2, 384>;
+    if (lanes_tpb() == 768 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 1, 768>;
     return count ? (KernelFn)render_kernel_lanes<ISECT, SMEM, true, false> : (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false>;
 }
 static KernelFn pick_kernel(int isect, bool smem, bool count) {
@@ -1225,7 +1238,10 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
     // spheres the 147 KB copy leaves one CTA per SM and loses to the L1/L2 path; profiles/r1_c5_sweep.log).
     static int smem_override = -2;  // RT_B200_SMEM=0|1 forces the choice (measurement only)
     if (smem_override == -2) smem_override = env_int("RT_B200_SMEM", -1);
-    bool smem = (need + static_smem + 1024) * 3 <= (size_t)smem_optin;
+    const bool lanes = bvh_variant() == 3 || bvh_variant() == 5;
+    const int threads = (lanes && !count && list_max_prims() == 0 && env_int("RT_B200_LANES_MINB", 3) != 4) ? lanes_tpb() : THREADS;
+    const int ctas_target = 768 / threads;  // 24 warps per SM
+    bool smem = (need + static_smem + 1024) * (size_t)ctas_target <= (size_t)smem_optin;
     if (smem_override == 0) smem = false;
     if (smem_override == 1) smem = need + static_smem + 1024 <= (size_t)smem_optin;
     KernelFn fn = pick_kernel(isect, smem, count);
@@ -1233,12 +1249,12 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, THREADS, dyn);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, dyn);
     if (e != cudaSuccess) return e;
     if (per_sm < 1) per_sm = 1;
     uint64_t total_tiles = (uint64_t)pr.tiles_x * pr.tiles_y;
     uint64_t my_tiles = (total_tiles + pr.tile_ranks - 1) / pr.tile_ranks;
-    uint64_t want_ctas = (my_tiles + WARPS - 1) / WARPS;
+    uint64_t want_ctas = (my_tiles + (threads / 32) - 1) / (threads / 32);
     uint64_t grid = (uint64_t)sm_count * per_sm;
     if (grid > want_ctas) grid = want_ctas;
     if (grid < 1) grid = 1;
@@ -1259,10 +1275,10 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
     static int rev = -1;  // RT_B200_TILE_ORDER=topdown restores the first hand-out order
     if (rev < 0) { const char* e = std::getenv("RT_B200_TILE_ORDER"); rev = (e && std::strcmp(e, "topdown") == 0) ? 0 : 1; }
     prm.tile_order_reverse = rev;
-    fn<<<(unsigned)grid, THREADS, dyn, stream>>>(sc, cam, prm);
+    fn<<<(unsigned)grid, threads, dyn, stream>>>(sc, cam, prm);
     if (info) {
         info->grid = (unsigned)grid;
-        info->threads = THREADS;
+        info->threads = threads;
         info->dyn_smem = dyn;
         info->ctas_per_sm = per_sm;
         info->scene_in_smem = smem;
