@@ -65,6 +65,31 @@ def test_host_bvh_matches_reference_leaf_order(O, rt):
     assert np.array_equal(api.bvh_build_host(sp, None)[0], O.leaf_order(sp, None)[0])
 
 
+def test_host_bvh_two_shape_shortcut_and_tiny_extents(O, rt):
+    """The host builder answers two-shape nodes in closed form (half of all nodes); it must agree with the bucket
+    machinery of bvh_impl.rs:229-364 (as restated by the oracle) when centroids tie, nearly tie (extent around the
+    crate's EPSILON = 1e-5) or sit on a coarse lattice."""
+    from rt_b200 import api, scenes
+
+    rng = np.random.default_rng(11)
+    for trial in range(120):
+        n = int(rng.integers(2, 40))
+        sp = scenes.synthetic_spheres(n, trial)
+        kind = trial % 4
+        if kind == 0:    # coarse lattice: many equal coordinates
+            sp["center"] = np.round(sp["center"] * 0.5) * 2.0
+        elif kind == 1:  # clusters with extents around EPSILON
+            base = rng.uniform(-5, 5, size=(1, 3)) + np.array([0, 0, -10.0])
+            sp["center"] = (base + rng.uniform(-1, 1, size=(n, 3)) * 10.0 ** rng.uniform(-7, -3)).astype(np.float32)
+        elif kind == 2:  # pairs of identical spheres
+            sp["center"][1::2] = sp["center"][0::2][: len(sp["center"][1::2])]
+        sp["radius"] = np.maximum(sp["radius"], 1e-3).astype(np.float32)
+        got = api.bvh_build_host(sp, None)
+        want = O.leaf_order(sp, None)
+        assert np.array_equal(got[0], want[0]), (trial, kind, n)
+        assert got[2] == want[1]
+
+
 def test_host_bvh_errors(rt):
     from rt_b200 import api, scenes
 
