@@ -119,8 +119,11 @@ struct Builder {
         while (d > cur && !max_depth.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {}
     }
 
-    // Builds the subtree over idx[lo,hi) into inner[base, base + n - 1) and returns its code.
-    int32_t build(size_t lo, size_t hi, uint32_t depth, size_t base) {
+    // Builds the subtree over idx[lo,hi) into inner[base, base + n - 1) and returns its code.  all_in / cent_in: the
+    // node's shape bounds and centroid bounds when the parent already has them (the joins of its buckets — min/max are
+    // exact and associative, so they equal a pass over the shapes up to the sign of a zero, which no decision sees).
+    int32_t build(size_t lo, size_t hi, uint32_t depth, size_t base, const Bounds* all_in = nullptr,
+                  const Bounds* cent_in = nullptr) {
         if (failed.load(std::memory_order_relaxed)) return 0;
         if (depth > 4096) {
             fail("BVH deeper than 4096 levels");
@@ -132,11 +135,16 @@ struct Builder {
             return ~(int32_t)idx[lo];
         }
         Bounds all, cent;
-        all.clear();
-        cent.clear();
-        for (size_t i = lo; i < hi; i++) {
-            all.join(boxes[idx[i]]);
-            cent.grow(&centre[3 * (size_t)idx[i]]);
+        if (all_in && cent_in) {
+            all = *all_in;
+            cent = *cent_in;
+        } else {
+            all.clear();
+            cent.clear();
+            for (size_t i = lo; i < hi; i++) {
+                all.join(boxes[idx[i]]);
+                cent.grow(&centre[3 * (size_t)idx[i]]);
+            }
         }
         const int32_t me = (int32_t)base;
 
@@ -146,7 +154,8 @@ struct Builder {
         const float extent = cent.hi[axis] - cent.lo[axis];
 
         size_t mid;
-        Bounds bl, br;
+        Bounds bl, br, cl, cr;
+        bool child_bounds = false;  // bl/br + cl/cr describe the children completely
         if (n == 2 && extent >= kEpsilon && extent < std::numeric_limits<float>::infinity()) {
             // Two shapes, finite extent (half of all nodes): the centroid at the low end has rel = 0 → bucket 0, the other
             // rel = extent/extent = 1 → bucket 5; every split gives the same cost and the first wins, so the children
@@ -164,9 +173,10 @@ struct Builder {
             for (size_t i = lo; i < mid; i++) bl.join(boxes[idx[i]]);
             for (size_t i = mid; i < hi; i++) br.join(boxes[idx[i]]);
         } else {
-            Bounds bb[kBuckets];
+            Bounds bb[kBuckets], bc[kBuckets];
             size_t cnt[kBuckets] = {0, 0, 0, 0, 0, 0};
             for (auto& b : bb) b.clear();
+            for (auto& b : bc) b.clear();
             for (size_t i = lo; i < hi; i++) {
                 const float* c = &centre[3 * (size_t)idx[i]];
                 const float rel = (c[axis] - cent.lo[axis]) / extent;
@@ -180,6 +190,7 @@ struct Builder {
                 bucket_of[i] = (uint8_t)k;
                 cnt[k]++;
                 bb[k].join(boxes[idx[i]]);
+                bc[k].grow(c);
             }
             int best = 0;
             float best_cost = std::numeric_limits<float>::infinity();
@@ -218,6 +229,11 @@ struct Builder {
             size_t nl = 0;
             for (int k = 0; k <= best; k++) nl += cnt[k];
             mid = lo + nl;
+            cl.clear();
+            cr.clear();
+            for (int k = 0; k <= best; k++) cl.join(bc[k]);
+            for (int k = best + 1; k < kBuckets; k++) cr.join(bc[k]);
+            child_bounds = true;
         }
         if (bl.empty() || br.empty() || mid == lo || mid == hi) {  // reference: assert!(!child_aabb.is_empty())
             fail("degenerate split (empty child bounds)");
@@ -225,12 +241,12 @@ struct Builder {
         }
         int32_t l = 0, r = 0;
         if (mid - lo >= kParallelMin && hi - mid >= kParallelMin) {
-            std::thread t([&] { l = build(lo, mid, depth + 1, base + 1); });
-            r = build(mid, hi, depth + 1, base + (mid - lo));
+            std::thread t([&] { l = build(lo, mid, depth + 1, base + 1, child_bounds ? &bl : nullptr, child_bounds ? &cl : nullptr); });
+            r = build(mid, hi, depth + 1, base + (mid - lo), child_bounds ? &br : nullptr, child_bounds ? &cr : nullptr);
             t.join();
         } else {
-            l = build(lo, mid, depth + 1, base + 1);
-            r = build(mid, hi, depth + 1, base + (mid - lo));
+            l = build(lo, mid, depth + 1, base + 1, child_bounds ? &bl : nullptr, child_bounds ? &cl : nullptr);
+            r = build(mid, hi, depth + 1, base + (mid - lo), child_bounds ? &br : nullptr, child_bounds ? &cr : nullptr);
         }
         HostNode& nd = out->inner[me];
         nd.box_l = bl.box();
