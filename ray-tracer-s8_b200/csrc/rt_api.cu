@@ -358,7 +358,8 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
         ctx->h_stage = nullptr;
         ctx->h_stage_bytes = 0;
-        const size_t cap = align_up(blob.n + blob.n / 2, 1 << 16);
+        size_t cap = (size_t)1 << 20;
+        while (cap < blob.n) cap <<= 1;
         CK(ctx, cudaMallocHost(&ctx->h_stage, cap));
         ctx->h_stage_bytes = cap;
     }
@@ -658,7 +659,11 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             sc->blob_cap = ctx->retired[pick].cap;
             ctx->retired.erase(ctx->retired.begin() + (long)pick);
         } else if (e == cudaSuccess) {
-            sc->blob_cap = align_up(blob.size(), 1 << 16);
+            // power-of-two size classes (>= 256 KB): retired blobs fit the next scene of a similar size, and the driver
+            // sees few distinct allocation sizes (cudaMalloc / cudaMallocHost stall for 50-200 ms now and then)
+            size_t cap = (size_t)1 << 18;
+            while (cap < blob.size()) cap <<= 1;
+            sc->blob_cap = cap;
             e = cudaMalloc(&sc->d_blob, sc->blob_cap);
         }
     }

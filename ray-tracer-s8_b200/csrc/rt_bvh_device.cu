@@ -204,11 +204,13 @@ cudaError_t build_lbvh_device(DeviceBuild* buf, const float* h_boxes, const uint
     if (buf->bytes < off) {
         cudaStreamSynchronize(stream);
         free_device_build(buf);
-        if ((e = cudaMalloc(&buf->mem, off)) != cudaSuccess) return e;
-        buf->bytes = off;
+        size_t cap = (size_t)1 << 20;
+        while (cap < off) cap <<= 1;
+        if ((e = cudaMalloc(&buf->mem, cap)) != cudaSuccess) return e;
+        buf->bytes = cap;
     }
     static const bool timing = std::getenv("RT_B200_TIMING") != nullptr;
-    if (timing) fprintf(stderr, "[build_lbvh_device n=%u] scratch %zu bytes (%s)\n", n, off, buf->bytes == off ? "new" : "reused");
+    if (timing) fprintf(stderr, "[build_lbvh_device n=%u] scratch %zu bytes of %zu\n", n, off, buf->bytes);
     uint8_t* m = (uint8_t*)buf->mem;
     float* d_boxes = (float*)(m + o_box);
     uint32_t* d_pid = (uint32_t*)(m + o_pid);
