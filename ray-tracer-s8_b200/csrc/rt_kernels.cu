@@ -1204,7 +1204,10 @@ static KernelFn pick_lanes(bool count) {
     if (ISECT == RT_INTERSECT_BVH && list_max_prims() > 0 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, true>;
     static int minb = -1;  // RT_B200_LANES_MINB=4: 64 registers, 32 resident warps per SM (experiment)
     if (minb < 0) minb = env_int("RT_B200_LANES_MINB", 3);
-    if (minb == 4 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 4>;
+    // scene read through L1/L2 (too large for shared memory): the BVH kernel is latency bound there, and 32 warps per SM at
+    // 64 registers beat 24 at 80 (65,536 spheres: 3.13 -> 2.84 ms; profiles/r1_notes.md)
+    const bool wide = !SMEM && ISECT == RT_INTERSECT_BVH && minb == 3;
+    if ((minb == 4 || wide) && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 4>;
     if (lanes_tpb() == 384 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 2, 384>;
     if (lanes_tpb() == 768 && !count) return (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 1, 768>;
     return count ? (KernelFn)render_kernel_lanes<ISECT, SMEM, true, false> : (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false>;
@@ -1239,11 +1242,12 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
     static int smem_override = -2;  // RT_B200_SMEM=0|1 forces the choice (measurement only)
     if (smem_override == -2) smem_override = env_int("RT_B200_SMEM", -1);
     const bool lanes = bvh_variant() == 3 || bvh_variant() == 5;
-    const int threads = (lanes && !count && list_max_prims() == 0 && env_int("RT_B200_LANES_MINB", 3) != 4) ? lanes_tpb() : THREADS;
+    int threads = (lanes && !count && list_max_prims() == 0 && env_int("RT_B200_LANES_MINB", 3) != 4) ? lanes_tpb() : THREADS;
     const int ctas_target = 768 / threads;  // 24 warps per SM
     bool smem = (need + static_smem + 1024) * (size_t)ctas_target <= (size_t)smem_optin;
     if (smem_override == 0) smem = false;
     if (smem_override == 1) smem = need + static_smem + 1024 <= (size_t)smem_optin;
+    if (!smem && isect == RT_INTERSECT_BVH) threads = THREADS;  // the 64-register variant runs 4 x 256 threads (pick_lanes)
     KernelFn fn = pick_kernel(isect, smem, count);
     size_t dyn = smem ? need : 0;
     cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn);
