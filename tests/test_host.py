@@ -90,6 +90,19 @@ def test_host_bvh_two_shape_shortcut_and_tiny_extents(O, rt):
         assert got[2] == want[1]
 
 
+def test_host_bvh_threaded_build_matches(O, rt):
+    """Above 2048 shapes per child the host builders hand subtrees to their own threads (node slots are known in
+    advance: a subtree of n shapes owns n - 1 consecutive pre-order slots); the result must not depend on that."""
+    from rt_b200 import api, scenes
+
+    sp = scenes.synthetic_spheres(20000, 3)
+    tr = scenes.ground_plane()
+    got = api.bvh_build_host(sp, tr)
+    want = O.leaf_order(sp, tr)
+    assert np.array_equal(got[0], want[0])
+    assert got[1] == 2 * 20002 - 1 and got[2] == want[1]
+
+
 def test_host_bvh_errors(rt):
     from rt_b200 import api, scenes
 
