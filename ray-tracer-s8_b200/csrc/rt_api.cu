@@ -3,6 +3,8 @@
 // Replaces the body of worker() in ray-tracer-slave/src/main.rs:32-106 (see the header for the mapping).
 // There is no CPU fallback anywhere in this file: every render goes through launch_render().
 #include <chrono>
+#include <functional>
+#include <thread>
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
@@ -191,7 +193,8 @@ inline bool finite3(const float* v) { return std::isfinite(v[0]) && std::isfinit
 // World order + bounds + BVH, shared by rt_scene_create and rt_bvh_build_host.  Host only.
 static int build_world_bvh(const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles,
                            uint32_t n_triangles, const uint32_t* world_index, std::vector<PrimRef>* world_out,
-                           HostBVH* bvh, std::string* err, std::vector<Box>* boxes_out = nullptr) {
+                           HostBVH* bvh, std::string* err, std::vector<Box>* boxes_out = nullptr,
+                           const std::function<void(const std::vector<Box>&)>* side_job = nullptr) {
     char buf[256];
     const uint32_t n = n_spheres + n_triangles;
     std::vector<PrimRef>& world = *world_out;
@@ -237,8 +240,21 @@ static int build_world_bvh(const rt_sphere* spheres, uint32_t n_spheres, const r
             }
         }
     }
+    // an independent job on the boxes (the traversal-tree build) runs beside the reference build when it is worth a thread
+    std::thread side;
+    bool side_done = false;
+    if (side_job && n >= 512) {
+        try {
+            side = std::thread([&] { (*side_job)(boxes); });
+            side_done = true;
+        } catch (...) {
+        }
+    }
     std::string berr;
-    if (!build_bvh(boxes, bvh, &berr)) {
+    const bool built = build_bvh(boxes, bvh, &berr);
+    if (side.joinable()) side.join();
+    if (side_job && !side_done) (*side_job)(boxes);
+    if (!built) {
         *err = "BVH build failed: " + berr;
         return RT_ERR_BVH;
     }
@@ -307,12 +323,98 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         fprintf(stderr, "[rt_scene_create n=%u] %-22s %8.3f ms\n", n, what, std::chrono::duration<double, std::milli>(now - t_prev).count());
         t_prev = now;
     };
+    std::vector<uint32_t> big_world;  // split layout: world positions of the primitives kept out of the tree
+    bool ltree = true;
+    // RT_B200_BUILD = auto (default) | host | device.  device: the traversal tree is an LBVH built on the GPU after the
+    // upload (rt_bvh_device.cu) instead of the host's binned-SAH tree; auto picks it from kDeviceBuildMin primitives,
+    // where the host build costs more than the LBVH's extra slab tests (profiles/r1_notes.md).
+    static const int build_mode = [] {
+        const char* e = std::getenv("RT_B200_BUILD");
+        return (e && std::strcmp(e, "host") == 0) ? 0 : ((e && std::strcmp(e, "device") == 0) ? 2 : 1);
+    }();
+    constexpr uint32_t kDeviceBuildMin = 8192;
+    bool device_tree = false;
+    std::vector<float> dev_boxes;     // boxes and pids of the primitives the device-built tree covers
+    std::vector<uint32_t> dev_pid;
+    HostBVH sah;
+    bool use_sah = false;
+    std::vector<uint32_t> dev_world;  // device-built tree: world positions of the primitives it covers
+    // Chooses and (on the host path) builds the traversal tree from the boxes alone, so it can run beside the reference build.
+    const std::function<void(const std::vector<Box>&)> select_tree = [&](const std::vector<Box>& boxes) {
+        // RT_B200_TREE = split (default) | sah | ref.  ref: the reference-topology tree itself.  sah: a 3-axis binned-SAH
+        // tree over all primitives.  split: the primitives whose box area is a large share of the whole scene's go to a
+        // short list tested ahead of the traversal, and the 3-axis SAH tree covers the rest (measured: profiles/).
+        const char* te = std::getenv("RT_B200_TREE");
+        int mode = 2;
+        if (te && std::strcmp(te, "ref") == 0) mode = 0;
+        if (te && std::strcmp(te, "sah") == 0) mode = 1;
+        if (mode == 2 && n > 1) {
+            auto area_of = [](const Box& b) {
+                const double sx = (double)b.max[0] - b.min[0], sy = (double)b.max[1] - b.min[1], sz = (double)b.max[2] - b.min[2];
+                return 2.0 * (sx * sy + sx * sz + sy * sz);
+            };
+            Box all = boxes[0];
+            for (uint32_t w = 1; w < n; w++)
+                for (int a = 0; a < 3; a++) {
+                    all.min[a] = fminf(all.min[a], boxes[w].min[a]);
+                    all.max[a] = fmaxf(all.max[a], boxes[w].max[a]);
+                }
+            const double thresh = area_of(all) * (1.0 / 16.0);
+            std::vector<std::pair<double, uint32_t>> cand;
+            for (uint32_t w = 0; w < n; w++) {
+                const double a = area_of(boxes[w]);
+                if (a > thresh && a > 0.0) cand.push_back({-a, w});
+            }
+            std::sort(cand.begin(), cand.end());
+            if (cand.size() > (size_t)MAX_BIG) cand.resize(MAX_BIG);
+            std::vector<uint8_t> is_big(n, 0);
+            for (auto& c : cand) {
+                big_world.push_back(c.second);
+                is_big[c.second] = 1;
+            }
+            std::sort(big_world.begin(), big_world.end());
+            std::vector<Box> rest;
+            std::vector<uint32_t> rest_world;
+            for (uint32_t w = 0; w < n; w++)
+                if (!is_big[w]) {
+                    rest.push_back(boxes[w]);
+                    rest_world.push_back(w);
+                }
+            if (rest.empty()) {
+                ltree = false;
+            } else if (rest.size() >= 2 && (build_mode == 2 || (build_mode == 1 && rest.size() >= kDeviceBuildMin))) {
+                device_tree = true;
+                dev_boxes.resize(6 * rest.size());
+                for (size_t i = 0; i < rest.size(); i++)
+                    for (int a = 0; a < 3; a++) {
+                        dev_boxes[6 * i + a] = rest[i].min[a];
+                        dev_boxes[6 * i + 3 + a] = rest[i].max[a];
+                    }
+                dev_world = rest_world;  // pids are filled in once the reference build has assigned them
+            } else {
+                use_sah = build_bvh_sah(rest, &sah) && sah.depth <= (uint32_t)MAX_STACK;
+                if (use_sah) {  // leaf codes: subset index → world position
+                    auto remap = [&](int32_t c) { return c >= 0 ? c : ~(int32_t)rest_world[(uint32_t)~c]; };
+                    for (auto& nd : sah.inner) {
+                        nd.left = remap(nd.left);
+                        nd.right = remap(nd.right);
+                    }
+                    sah.root = remap(sah.root);
+                } else {
+                    big_world.clear();  // fall back to the reference tree over everything
+                }
+            }
+        } else if (mode == 1) {
+            use_sah = build_bvh_sah(boxes, &sah) && sah.depth <= (uint32_t)MAX_STACK;
+        }
+    };
     std::vector<PrimRef> world;
     std::vector<Box> boxes;  // the reference's (unpadded) shape AABBs by world position
     HostBVH bvh;
     {
         std::string herr;
-        int hrc = build_world_bvh(spheres, n_spheres, triangles, n_triangles, world_index, &world, &bvh, &herr, &boxes);
+        int hrc = build_world_bvh(spheres, n_spheres, triangles, n_triangles, world_index, &world, &bvh, &herr, &boxes,
+                                  &select_tree);
         if (hrc) return set_err(ctx, hrc, "%s", herr.c_str());
     }
     // pids: spheres then triangles, each in DFS leaf order
@@ -324,6 +426,10 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         pid_of_world[w] = world[w].kind == 0 ? next_s++ : next_t++;
     }
     const uint32_t ni = (uint32_t)bvh.inner.size();
+    if (device_tree) {
+        dev_pid.resize(dev_world.size());
+        for (size_t i = 0; i < dev_world.size(); i++) dev_pid[i] = pid_of_world[dev_world[i]];
+    }
     lap("reference-tree build");
 
     // blob layout (each section 256-byte aligned)
@@ -475,90 +581,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     //      subtrees of <= L same-kind primitives into one leaf (only with the reference tree, whose DFS order = pid order).
     uint32_t lni = 0;
     int32_t lroot = 0;
-    std::vector<uint32_t> big_world;  // split layout: world positions of the primitives kept out of the tree
-    bool ltree = true;
-    // RT_B200_BUILD = auto (default) | host | device.  device: the traversal tree is an LBVH built on the GPU after the
-    // upload (rt_bvh_device.cu) instead of the host's binned-SAH tree; auto picks it from kDeviceBuildMin primitives,
-    // where the host build costs more than the LBVH's extra slab tests (profiles/r1_notes.md).
-    static const int build_mode = [] {
-        const char* e = std::getenv("RT_B200_BUILD");
-        return (e && std::strcmp(e, "host") == 0) ? 0 : ((e && std::strcmp(e, "device") == 0) ? 2 : 1);
-    }();
-    constexpr uint32_t kDeviceBuildMin = 8192;
-    bool device_tree = false;
-    std::vector<float> dev_boxes;     // boxes and pids of the primitives the device-built tree covers
-    std::vector<uint32_t> dev_pid;
     {
-        // RT_B200_TREE = split (default) | sah | ref.  ref: the reference-topology tree itself.  sah: a 3-axis binned-SAH
-        // tree over all primitives.  split: the primitives whose box area is a large share of the whole scene's go to a
-        // short list tested ahead of the traversal, and the 3-axis SAH tree covers the rest (measured: profiles/).
-        const char* te = std::getenv("RT_B200_TREE");
-        int mode = 2;
-        if (te && std::strcmp(te, "ref") == 0) mode = 0;
-        if (te && std::strcmp(te, "sah") == 0) mode = 1;
-        HostBVH sah;
-        bool use_sah = false;
-        if (mode == 2 && n > 1) {
-            auto area_of = [](const Box& b) {
-                const double sx = (double)b.max[0] - b.min[0], sy = (double)b.max[1] - b.min[1], sz = (double)b.max[2] - b.min[2];
-                return 2.0 * (sx * sy + sx * sz + sy * sz);
-            };
-            Box all = boxes[0];
-            for (uint32_t w = 1; w < n; w++)
-                for (int a = 0; a < 3; a++) {
-                    all.min[a] = fminf(all.min[a], boxes[w].min[a]);
-                    all.max[a] = fmaxf(all.max[a], boxes[w].max[a]);
-                }
-            const double thresh = area_of(all) * (1.0 / 16.0);
-            std::vector<std::pair<double, uint32_t>> cand;
-            for (uint32_t w = 0; w < n; w++) {
-                const double a = area_of(boxes[w]);
-                if (a > thresh && a > 0.0) cand.push_back({-a, w});
-            }
-            std::sort(cand.begin(), cand.end());
-            if (cand.size() > (size_t)MAX_BIG) cand.resize(MAX_BIG);
-            std::vector<uint8_t> is_big(n, 0);
-            for (auto& c : cand) {
-                big_world.push_back(c.second);
-                is_big[c.second] = 1;
-            }
-            std::sort(big_world.begin(), big_world.end());
-            std::vector<Box> rest;
-            std::vector<uint32_t> rest_world;
-            for (uint32_t w = 0; w < n; w++)
-                if (!is_big[w]) {
-                    rest.push_back(boxes[w]);
-                    rest_world.push_back(w);
-                }
-            if (rest.empty()) {
-                ltree = false;
-            } else if (rest.size() >= 2 && (build_mode == 2 || (build_mode == 1 && rest.size() >= kDeviceBuildMin))) {
-                device_tree = true;
-                dev_boxes.resize(6 * rest.size());
-                dev_pid.resize(rest.size());
-                for (size_t i = 0; i < rest.size(); i++) {
-                    for (int a = 0; a < 3; a++) {
-                        dev_boxes[6 * i + a] = rest[i].min[a];
-                        dev_boxes[6 * i + 3 + a] = rest[i].max[a];
-                    }
-                    dev_pid[i] = pid_of_world[rest_world[i]];
-                }
-            } else {
-                use_sah = build_bvh_sah(rest, &sah) && sah.depth <= (uint32_t)MAX_STACK;
-                if (use_sah) {  // leaf codes: subset index → world position
-                    auto remap = [&](int32_t c) { return c >= 0 ? c : ~(int32_t)rest_world[(uint32_t)~c]; };
-                    for (auto& nd : sah.inner) {
-                        nd.left = remap(nd.left);
-                        nd.right = remap(nd.right);
-                    }
-                    sah.root = remap(sah.root);
-                } else {
-                    big_world.clear();  // fall back to the reference tree over everything
-                }
-            }
-        } else if (mode == 1) {
-            use_sah = build_bvh_sah(boxes, &sah) && sah.depth <= (uint32_t)MAX_STACK;
-        }
         const HostBVH& T = use_sah ? sah : bvh;
         int L = 1;  // measured on C3 (reference tree): 1 → 51.8 ms, 4 → 54.6, 16 → 62.7 (profiles/)
         if (const char* e = std::getenv("RT_B200_LEAF")) L = std::atoi(e);
