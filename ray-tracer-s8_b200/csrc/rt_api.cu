@@ -284,7 +284,7 @@ int rt_bvh_build_host(const rt_sphere* spheres, uint32_t n_spheres, const rt_tri
                       const uint32_t* world_index, uint32_t* rank_out, uint32_t* n_nodes, uint32_t* depth) {
     const uint64_t n64 = (uint64_t)n_spheres + n_triangles;
     if (n64 == 0) return RT_ERR_EMPTY_SCENE;
-    if (n64 > 0x3fffffffu) return RT_ERR_UNSUPPORTED;
+    if (n64 > 0x3ffffffu) return RT_ERR_UNSUPPORTED;  // leaf codes hold a 26-bit primitive id
     if ((n_spheres && !spheres) || (n_triangles && !triangles)) return RT_ERR_INVALID_ARG;
     std::vector<PrimRef> world;
     HostBVH bvh;
@@ -310,7 +310,8 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     if (n64 == 0)
         return set_err(ctx, RT_ERR_EMPTY_SCENE,
                        "empty world: the reference's BVHNode::build never terminates on zero shapes");
-    if (n64 > 0x3fffffffu) return set_err(ctx, RT_ERR_UNSUPPORTED, "too many primitives");
+    if (n64 > 0x3ffffffu)  // leaf codes are ~((first_pid << 5) | (count - 1)) in 32 bits
+        return set_err(ctx, RT_ERR_UNSUPPORTED, "too many primitives (%llu; this build holds primitive ids in 26 bits)", (unsigned long long)n64);
     if ((n_spheres && !spheres) || (n_triangles && !triangles))
         return set_err(ctx, RT_ERR_INVALID_ARG, "rt_scene_create: NULL primitive array");
     const uint32_t n = (uint32_t)n64;
