@@ -180,6 +180,12 @@ int rt_frame_download(rt_ctx* ctx, const void* frame_dev, uint8_t* out_rgb, size
 /* FFMA-chain micro-benchmark: achieved FP32 TFLOP/s (2 flops per FFMA) on this device, for the
  * roofline denominator (MEASURED_PEAKS.json has no CUDA-core figure). */
 int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops_out, float* ms_out);
+/* Trace-only benchmark (development aid, csrc/rt_trace_bench.cuh): renders one frame while recording up to max_rays of
+ * its nearest-hit queries, then times the query alone over the recorded rays as (a) the product kernel's while-while
+ * traversal and (b) a ballot-scheduled state machine with dynamic fetch, and counts rays whose answers differ.
+ * with_big = 0 leaves the split layout's big primitives out of both.  The scene must fit shared memory. */
+int rt_debug_trace_bench(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint64_t max_rays, int with_big,
+                         uint64_t* n_rays_out, float* ms_while_while, float* ms_state_machine, uint64_t* mismatches_out);
 /* Device properties: sm_count, clock_khz (max SM clock), smem_optin bytes. Nullable outputs. */
 int rt_device_info(rt_ctx* ctx, int* sm_count, int* clock_khz, int* smem_optin, char name_out[64]);
 

@@ -33,6 +33,10 @@ struct rt_ctx {
     WaveBuffers wave;
     WqBuffers wq;
     DeviceBuild dbuild;
+    // measurement aid: when set, the instrumented render kernel records its queries here (rt_debug_trace_bench)
+    float4* dump_rays = nullptr;
+    unsigned long long* dump_n = nullptr;
+    unsigned long long dump_cap = 0;
     // scene upload: one pinned staging buffer the blob is assembled in, and a few retired device blobs kept for the
     // next rt_scene_create (a slave makes one scene per job: cudaMalloc/cudaFree per job were a third of a small job)
     uint8_t* h_stage = nullptr;
@@ -855,6 +859,9 @@ int launch(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, uint32_t row0,
     pr.out_row0 = out_row0;
     pr.tiles_x = (r.p.width + TILE_W - 1) / TILE_W;
     pr.tiles_y = (row1 - row0 + TILE_H - 1) / TILE_H;
+    pr.ray_dump = ctx->dump_rays;
+    pr.ray_dump_n = ctx->dump_n;
+    pr.ray_dump_cap = ctx->dump_cap;
     pr.counters = ctx->d_ctr;
     pr.tile_counter = reinterpret_cast<unsigned int*>(ctx->d_ctr + NUM_COUNTERS);
     CK(ctx, cudaMemsetAsync(ctx->d_ctr, 0, (NUM_COUNTERS + 1) * sizeof(unsigned long long), ctx->stream));
@@ -1061,6 +1068,95 @@ int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops_out, float* ms_out) {
     const double flops = (double)ctx->sm_count * 8 * 256 * (double)iters * 16 * 8 * 2;
     *tflops_out = flops / (best * 1e-3) / 1e12;
     if (ms_out) *ms_out = best;
+    return RT_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// Trace-only benchmark (csrc/rt_trace_bench.cuh): record the queries of one frame, then time the nearest-hit query
+// alone in two forms over the recorded rays and compare their answers.
+// -------------------------------------------------------------------------------------------------
+int rt_debug_trace_bench(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint64_t max_rays, int with_big,
+                         uint64_t* n_rays_out, float* ms_while_while, float* ms_state_machine, uint64_t* mismatches_out) {
+    if (!ctx || !scene || !params || !n_rays_out || !ms_while_while || !ms_state_machine || !mismatches_out)
+        return RT_ERR_INVALID_ARG;
+    if (max_rays == 0) return set_err(ctx, RT_ERR_INVALID_ARG, "max_rays is 0");
+    rt_params p = *params;
+    p.collect_counters = 1;
+    p.intersector = RT_INTERSECT_BVH;
+    Resolved r;
+    int rc = resolve(ctx, scene, &p, &r);
+    if (rc) return rc;
+    CK(ctx, cudaSetDevice(ctx->device));
+    rc = ensure_out(ctx, (size_t)r.p.width * r.p.height * 3);
+    if (rc) return rc;
+    float4* d_rays = nullptr;
+    unsigned long long* d_cnt = nullptr;  // [0] recorded queries, [1] ticket
+    int2 *d_out0 = nullptr, *d_out1 = nullptr;
+    auto cleanup = [&] {
+        ctx->dump_rays = nullptr;
+        ctx->dump_n = nullptr;
+        ctx->dump_cap = 0;
+        cudaFree(d_rays);
+        cudaFree(d_cnt);
+        cudaFree(d_out0);
+        cudaFree(d_out1);
+    };
+#define CKC(call)                                                                                      \
+    do {                                                                                               \
+        cudaError_t e__ = (call);                                                                      \
+        if (e__ != cudaSuccess) {                                                                      \
+            cleanup();                                                                                 \
+            return set_err(ctx, RT_ERR_CUDA, "%s: %s", #call, cudaGetErrorString(e__));                \
+        }                                                                                              \
+    } while (0)
+    CKC(cudaMalloc(&d_rays, (size_t)max_rays * 32));
+    CKC(cudaMalloc(&d_cnt, 16));
+    CKC(cudaMemsetAsync(d_cnt, 0, 16, ctx->stream));
+    ctx->dump_rays = d_rays;
+    ctx->dump_n = d_cnt;
+    ctx->dump_cap = max_rays;
+    LaunchInfo li;
+    rc = launch(ctx, scene, r, 0, r.p.height, 0, 1, ctx->d_out, 0, &li);
+    ctx->dump_rays = nullptr;
+    ctx->dump_n = nullptr;
+    ctx->dump_cap = 0;
+    if (rc) {
+        cleanup();
+        return rc;
+    }
+    unsigned long long recorded = 0;
+    CKC(cudaMemcpyAsync(&recorded, d_cnt, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CKC(cudaStreamSynchronize(ctx->stream));
+    const unsigned long long n = recorded < max_rays ? recorded : max_rays;
+    if (n == 0) {
+        cleanup();
+        return set_err(ctx, RT_ERR_INVALID_ARG, "no query was recorded");
+    }
+    CKC(cudaMalloc(&d_out0, (size_t)n * 8));
+    CKC(cudaMalloc(&d_out1, (size_t)n * 8));
+    float best[2] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};
+    for (int variant = 0; variant < 2; variant++)
+        for (int rep = 0; rep < 3; rep++) {
+            CKC(cudaEventRecord(ctx->ev0, ctx->stream));
+            CKC(launch_trace_bench(scene->dev, variant, with_big != 0, d_rays, n, d_cnt + 1, variant ? d_out1 : d_out0,
+                                   ctx->sm_count, ctx->smem_optin, ctx->stream));
+            CKC(cudaEventRecord(ctx->ev1, ctx->stream));
+            CKC(cudaStreamSynchronize(ctx->stream));
+            float ms = 0.0f;
+            CKC(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
+            if (ms < best[variant]) best[variant] = ms;
+        }
+    std::vector<int2> h0((size_t)n), h1((size_t)n);
+    CKC(cudaMemcpy(h0.data(), d_out0, (size_t)n * 8, cudaMemcpyDeviceToHost));
+    CKC(cudaMemcpy(h1.data(), d_out1, (size_t)n * 8, cudaMemcpyDeviceToHost));
+#undef CKC
+    uint64_t bad = 0;
+    for (size_t i = 0; i < (size_t)n; i++) bad += (h0[i].x != h1[i].x || h0[i].y != h1[i].y) ? 1 : 0;
+    cleanup();
+    *n_rays_out = n;
+    *ms_while_while = best[0];
+    *ms_state_machine = best[1];
+    *mismatches_out = bad;
     return RT_OK;
 }
 

@@ -81,6 +81,10 @@ struct DevParams {
     int sched_node_num, sched_node_den;
     int tile_order_reverse;      // 1: tickets walk the tile grid from the last tile to the first
     int list_max_prims;          // primary-ray candidate lists are built when the scene has at most this many primitives
+    // measurement aid (COUNT instantiation only): every query's ray is appended here (rt_trace_bench.cuh)
+    float4* ray_dump;
+    unsigned long long* ray_dump_n;
+    unsigned long long ray_dump_cap;
 };
 
 enum CounterSlot {

@@ -60,6 +60,8 @@ bool use_wavefront(int isect);
 bool legacy_node_arrays_needed();  // true when RT_B200_BVH_KERNEL selects a kernel that reads node_* / cnode_*
 cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevParams& pr, int isect, bool count,
                           int sm_count, int smem_optin, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_trace_bench(const DevScene& sc, int variant, bool with_big, const float4* rays, unsigned long long n,
+                               unsigned long long* ticket, int2* out, int sm_count, int smem_optin, cudaStream_t stream);
 cudaError_t launch_fp32_peak(float* scratch, int sm_count, int iters, cudaStream_t stream);
 size_t scene_smem_bytes(const DevScene& sc, int isect);
 

@@ -697,7 +697,7 @@ __global__ void __launch_bounds__(THREADS) render_kernel(const DevScene sc, cons
 // front of the exact triangle test.  Same while-while structure, same results.
 // ---------------------------------------------------------------------------------------------
 constexpr int TR_DONE = (int)0x80000000;  // traversal finished (never a leaf code: first_pid < 2^26)
-template <bool COUNT>
+template <bool COUNT, bool WITH_BIG = true>
 __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
     best.pid = -1;
     best.dist = 0.0f;
@@ -719,7 +719,7 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
     int cur = sc.lroot;
     const int ns = (int)sc.ns;
     // split layout: the large primitives first (their hits shorten everything that follows)
-    for (uint32_t i = 0; i < sc.nbig; i++) {
+    for (uint32_t i = 0; WITH_BIG && i < sc.nbig; i++) {
         const int pid = (int)sc.big_pid[i];
         if (pid < ns) {
             test_sphere<COUNT>(sc, sv.sph[pid], pid, o, d, best, ctr);
@@ -1032,6 +1032,16 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                 ctr.v[CTR_ACTIVE_LANES]++;
                 unsigned am = __activemask();
                 if (lane == (__ffs(am) - 1)) ctr.v[CTR_TOTAL_LANES] += 32;
+                if (pr.ray_dump) {  // measurement aid: record the query (one atomic per warp)
+                    unsigned long long base = 0;
+                    if (lane == (__ffs(am) - 1)) base = atomicAdd(pr.ray_dump_n, (unsigned long long)__popc(am));
+                    base = __shfl_sync(am, base, __ffs(am) - 1);
+                    const unsigned long long at = base + __popc(am & lt_mask);
+                    if (at < pr.ray_dump_cap) {
+                        pr.ray_dump[2 * at] = make_float4(o.x, o.y, o.z, d.x);
+                        pr.ray_dump[2 * at + 1] = make_float4(d.y, d.z, 0.0f, 0.0f);
+                    }
+                }
             }
             Hit h;
             if (ISECT == RT_INTERSECT_BRUTE) {
@@ -1125,6 +1135,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
 #include "rt_kernel_deferred.cuh"
 #include "rt_wavefront.cuh"
 #include "rt_kernel_wq.cuh"
+#include "rt_trace_bench.cuh"
 namespace rtb {
 
 // ---------------------------------------------------------------------------------------------
@@ -1466,6 +1477,36 @@ cudaError_t launch_wq(const DevScene& sc, const DevCamera& cam, const DevParams&
         info->dyn_smem = dyn;
         info->ctas_per_sm = 1;
         info->scene_in_smem = smem;
+    }
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------------------------
+// Trace-only benchmark (rt_trace_bench.cuh)
+// ---------------------------------------------------------------------------------------------
+cudaError_t launch_trace_bench(const DevScene& sc, int variant, bool with_big, const float4* rays, unsigned long long n,
+                               unsigned long long* ticket, int2* out, int sm_count, int smem_optin, cudaStream_t stream) {
+    const size_t need = (size_t)sc.ns * 16 + (size_t)sc.nt * 64 + (size_t)sc.lni * 56 + 16;
+    if (need + 1024 > (size_t)smem_optin) return cudaErrorInvalidValue;  // the benchmark reads the scene from shared memory
+    TbArgs a{};
+    a.rays = rays;
+    a.n = n;
+    a.ticket = ticket;
+    a.out = out;
+    a.node_burst = (uint32_t)env_int("RT_B200_WQ_BURST", 4);
+    a.t_leaf = (uint32_t)env_int("RT_B200_WQ_T_LEAF", 4);
+    a.t_pend = (uint32_t)env_int("RT_B200_WQ_T_PEND", 6);
+    a.t_fin = (uint32_t)env_int("RT_B200_WQ_T_FIN", 6);
+    cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream);
+    if (e != cudaSuccess) return e;
+    DevScene s2 = sc;
+    if (!with_big) s2.nbig = 0;  // the tree alone (a wavefront's LOGIC kernel would test the big primitives)
+    if (variant == 0) {
+        if ((e = cudaFuncSetAttribute(tb_ww, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)) != cudaSuccess) return e;
+        tb_ww<<<sm_count, 768, need, stream>>>(s2, a);
+    } else {
+        if ((e = cudaFuncSetAttribute(tb_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)) != cudaSuccess) return e;
+        tb_sm<<<sm_count, 768, need, stream>>>(s2, a);
     }
     return cudaGetLastError();
 }

@@ -64,6 +64,7 @@ EXPORTS = [
     "rt_scene_info", "rt_render_division", "rt_render_frame", "rt_render_tiles_device", "rt_sync", "rt_stream",
     "rt_host_alloc", "rt_host_free", "rt_frame_alloc", "rt_frame_open", "rt_frame_close", "rt_frame_free",
     "rt_frame_download", "rt_measure_fp32_peak", "rt_device_info", "rt_bvh_build_host", "rt_struct_sizes", "rt_scene_device_bytes",
+    "rt_debug_trace_bench",
 ]
 
 _lib = None
@@ -125,6 +126,9 @@ def lib():
     L.rt_frame_download.restype = i32
     L.rt_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.rt_measure_fp32_peak.restype = i32
+    L.rt_debug_trace_bench.argtypes = [vp, vp, C.c_void_p, C.c_uint64, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_float),
+                                       C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+    L.rt_debug_trace_bench.restype = i32
     L.rt_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.c_char_p]
     L.rt_device_info.restype = i32
     L.rt_bvh_build_host.argtypes = [vp, u32, vp, u32, vp, vp, C.POINTER(u32), C.POINTER(u32)]

@@ -100,6 +100,14 @@ class Context:
         self._check(self._lib.rt_measure_fp32_peak(self._h, C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
+    def trace_bench(self, scene: "Scene", params: RtParams, max_rays: int, with_big: bool = True):
+        """Development aid: the nearest-hit query alone over the recorded queries of one frame (rt_trace_bench.cuh)."""
+        n, bad = C.c_uint64(), C.c_uint64()
+        ms_ww, ms_sm = C.c_float(), C.c_float()
+        self._check(self._lib.rt_debug_trace_bench(self._h, scene._h, C.byref(params), int(max_rays), 1 if with_big else 0,
+                                                   C.byref(n), C.byref(ms_ww), C.byref(ms_sm), C.byref(bad)))
+        return {"rays": n.value, "ms_while_while": ms_ww.value, "ms_state_machine": ms_sm.value, "mismatches": bad.value}
+
     def sync(self):
         self._check(self._lib.rt_sync(self._h))
 
