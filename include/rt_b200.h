@@ -180,7 +180,7 @@ int rt_frame_download(rt_ctx* ctx, const void* frame_dev, uint8_t* out_rgb, size
 /* FFMA-chain micro-benchmark: achieved FP32 TFLOP/s (2 flops per FFMA) on this device, for the
  * roofline denominator (MEASURED_PEAKS.json has no CUDA-core figure). */
 int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops_out, float* ms_out);
-/* Trace-only benchmark (development aid, csrc/rt_trace_bench.cuh): renders one frame while recording up to max_rays of
+/* Trace-only benchmark (development aid, csrc/rt_trace_bench.cuh; with_big 2 / 3 = 0 / 1 on rays sorted by octant + cell): renders one frame while recording up to max_rays of
  * its nearest-hit queries, then times the query alone over the recorded rays as (a) the product kernel's while-while
  * traversal and (b) a ballot-scheduled state machine with dynamic fetch, and counts rays whose answers differ.
  * with_big = 0 leaves the split layout's big primitives out of both.  The scene must fit shared memory. */

@@ -1132,6 +1132,17 @@ int rt_debug_trace_bench(rt_ctx* ctx, const rt_scene* scene, const rt_params* pa
         cleanup();
         return set_err(ctx, RT_ERR_INVALID_ARG, "no query was recorded");
     }
+    if (with_big >= 2) {  // with_big = 2 | 3: as 0 | 1, on the rays sorted by direction octant and origin cell
+        float4* d_sorted = nullptr;
+        CKC(cudaMalloc(&d_sorted, (size_t)n * 32));
+        const float lo[3] = {-30.0f, -6.0f, -40.0f}, hi[3] = {30.0f, 12.0f, 2.0f};  // the BASELINE scenes' extent
+        const cudaError_t se = sort_rays_device(d_rays, n, lo, hi, d_sorted, ctx->stream);
+        if (se != cudaSuccess) cudaFree(d_sorted);
+        CKC(se);
+        cudaFree(d_rays);
+        d_rays = d_sorted;
+        with_big -= 2;
+    }
     CKC(cudaMalloc(&d_out0, (size_t)n * 8));
     CKC(cudaMalloc(&d_out1, (size_t)n * 8));
     float best[2] = {std::numeric_limits<float>::max(), std::numeric_limits<float>::max()};

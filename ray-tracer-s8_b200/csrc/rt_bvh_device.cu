@@ -164,6 +164,59 @@ size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
 
+// ---- measurement aid for rt_debug_trace_bench: reorder recorded rays by (direction octant, origin cell) -----------
+namespace {
+__global__ void ray_keys(const float4* __restrict__ rays, unsigned long long n, float3 lo, float3 scale,
+                         unsigned int* __restrict__ keys, unsigned int* __restrict__ idx) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 r0 = rays[2 * i], r1 = rays[2 * i + 1];
+    const uint32_t qx = (uint32_t)fminf(fmaxf((r0.x - lo.x) * scale.x, 0.0f), 127.0f);
+    const uint32_t qy = (uint32_t)fminf(fmaxf((r0.y - lo.y) * scale.y, 0.0f), 127.0f);
+    const uint32_t qz = (uint32_t)fminf(fmaxf((r0.z - lo.z) * scale.z, 0.0f), 127.0f);
+    const uint32_t oct = (r0.w < 0.0f ? 1u : 0u) | (r1.x < 0.0f ? 2u : 0u) | (r1.y < 0.0f ? 4u : 0u);
+    const uint32_t cell = (expand10(qx) << 2) | (expand10(qy) << 1) | expand10(qz);  // 21 bits
+    keys[i] = (oct << 21) | cell;
+    idx[i] = (unsigned int)i;
+}
+__global__ void ray_gather(const float4* __restrict__ in, const unsigned int* __restrict__ idx, unsigned long long n,
+                           float4* __restrict__ out) {
+    const unsigned long long i = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const unsigned long long j = idx[i];
+    out[2 * i] = in[2 * j];
+    out[2 * i + 1] = in[2 * j + 1];
+}
+}  // namespace
+
+// Sorts n recorded rays (2 float4 each) by direction octant, then by the Morton code of the origin's cell in a 128^3 grid
+// over [lo, hi].  `out` receives the reordered rays.  Scratch is allocated and freed here (one-off measurement).
+cudaError_t sort_rays_device(const float4* rays, unsigned long long n, const float lo[3], const float hi[3], float4* out,
+                             cudaStream_t stream) {
+    if (n == 0 || n > 0xffffffffull) return cudaErrorInvalidValue;
+    unsigned int *k0 = nullptr, *k1 = nullptr, *i0 = nullptr, *i1 = nullptr;
+    void* tmp = nullptr;
+    size_t tmp_bytes = 0;
+    cudaError_t e = cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, k0, k1, i0, i1, (int)n, 0, 24, stream);
+    if (e == cudaSuccess) e = cudaMalloc(&k0, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&k1, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&i0, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&i1, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&tmp, tmp_bytes);
+    if (e == cudaSuccess) {
+        const float3 l = make_float3(lo[0], lo[1], lo[2]);
+        const float3 sc = make_float3(127.999f / fmaxf(hi[0] - lo[0], 1e-20f), 127.999f / fmaxf(hi[1] - lo[1], 1e-20f),
+                                      127.999f / fmaxf(hi[2] - lo[2], 1e-20f));
+        const unsigned G = (unsigned)((n + 255) / 256);
+        ray_keys<<<G, 256, 0, stream>>>(rays, n, l, sc, k0, i0);
+        e = cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, k0, k1, i0, i1, (int)n, 0, 24, stream);
+        if (e == cudaSuccess) ray_gather<<<G, 256, 0, stream>>>(rays, i1, n, out);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    }
+    cudaFree(k0); cudaFree(k1); cudaFree(i0); cudaFree(i1); cudaFree(tmp);
+    return e;
+}
+
 void free_device_build(DeviceBuild* b) {
     if (b->mem) cudaFree(b->mem);
     *b = DeviceBuild();

@@ -53,6 +53,9 @@ void free_device_build(DeviceBuild* b);
 cudaError_t build_lbvh_device(DeviceBuild* buf, const float* h_boxes, const uint32_t* h_pid_of, uint32_t n,
                               float4* lnode_abc, int2* lnode_d, uint32_t* depth_out, cudaStream_t stream);
 
+cudaError_t sort_rays_device(const float4* rays, unsigned long long n, const float lo[3], const float hi[3], float4* out,
+                             cudaStream_t stream);
+
 // rt_kernels.cu
 cudaError_t launch_wavefront(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
                              int smem_optin, cudaStream_t stream, WaveBuffers* wb, LaunchInfo* info);

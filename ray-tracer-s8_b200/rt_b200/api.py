@@ -100,11 +100,11 @@ class Context:
         self._check(self._lib.rt_measure_fp32_peak(self._h, C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
-    def trace_bench(self, scene: "Scene", params: RtParams, max_rays: int, with_big: bool = True):
+    def trace_bench(self, scene: "Scene", params: RtParams, max_rays: int, with_big: bool = True, sort: bool = False):
         """Development aid: the nearest-hit query alone over the recorded queries of one frame (rt_trace_bench.cuh)."""
         n, bad = C.c_uint64(), C.c_uint64()
         ms_ww, ms_sm = C.c_float(), C.c_float()
-        self._check(self._lib.rt_debug_trace_bench(self._h, scene._h, C.byref(params), int(max_rays), 1 if with_big else 0,
+        self._check(self._lib.rt_debug_trace_bench(self._h, scene._h, C.byref(params), int(max_rays), (1 if with_big else 0) + (2 if sort else 0),
                                                    C.byref(n), C.byref(ms_ww), C.byref(ms_sm), C.byref(bad)))
         return {"rays": n.value, "ms_while_while": ms_ww.value, "ms_state_machine": ms_sm.value, "mismatches": bad.value}
 

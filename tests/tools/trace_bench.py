@@ -13,9 +13,9 @@ sp, tr = scenes.config_scene(name)
 ctx = rt.Context(0)
 sc = ctx.scene(sp, tr)
 p = rt.make_params(cfg["width"], cfg["height"], spp=cfg["spp"], max_bounces=cfg["max_bounces"], intersector=2)
-for with_big in (True, False):
-    r = ctx.trace_bench(sc, p, cap, with_big)
+for with_big, srt in ((True, False), (False, False), (False, True)):
+    r = ctx.trace_bench(sc, p, cap, with_big, srt)
     n = r["rays"]
-    print(f"{name} with_big={int(with_big)} rays={n} mismatches={r['mismatches']} "
+    print(f"{name} with_big={int(with_big)} sorted={int(srt)} rays={n} mismatches={r['mismatches']} "
           f"while-while {r['ms_while_while']:.3f} ms ({n / r['ms_while_while'] / 1e3:.0f} Mrays/s)  "
           f"state machine {r['ms_state_machine']:.3f} ms ({n / r['ms_state_machine'] / 1e3:.0f} Mrays/s)")
