@@ -11,7 +11,8 @@
 //            retire + refill served when enough lanes wait) with dynamic fetch from ONE global queue
 //
 // Both read the scene from shared memory (one 768-thread CTA per SM) and write (pid, length(p - o)) per ray; the host
-// compares the two outputs.  The big primitives of the split layout are tested by both at the start of a ray.
+// compares the two outputs.  The big primitives of the split layout are tested by both at the start of a ray (tb_ww: by
+// all 32 lanes together; tb_sm: at refill, by the lanes that refill) or by neither (with_big = 0: the tree alone).
 #pragma once
 
 namespace rtb {
@@ -21,7 +22,6 @@ struct TbArgs {
     unsigned long long n;
     unsigned long long* ticket;  // zeroed before launch
     int2* out;            // pid, dist bits
-    uint32_t min_active_unused;
     uint32_t node_burst, t_leaf, t_pend, t_fin;
 };
 
