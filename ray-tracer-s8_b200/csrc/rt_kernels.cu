@@ -1497,13 +1497,17 @@ cudaError_t launch_trace_bench(const DevScene& sc, int variant, bool with_big, c
     a.t_leaf = (uint32_t)env_int("RT_B200_WQ_T_LEAF", 4);
     a.t_pend = (uint32_t)env_int("RT_B200_WQ_T_PEND", 6);
     a.t_fin = (uint32_t)env_int("RT_B200_WQ_T_FIN", 6);
+    a.alt = (uint32_t)env_int("RT_B200_TB_ALT", 0);
+    a.sstack_off = (uint32_t)(need / 4);
+    const size_t need_ww = need + (a.alt ? (size_t)TB_SSTACK * 768 * 4 : 0);
+    if (a.alt && (need_ww + 1024 > (size_t)smem_optin || sc.lni == 0)) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     DevScene s2 = sc;
     if (!with_big) s2.nbig = 0;  // the tree alone (a wavefront's LOGIC kernel would test the big primitives)
     if (variant == 0) {
-        if ((e = cudaFuncSetAttribute(tb_ww, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)) != cudaSuccess) return e;
-        tb_ww<<<sm_count, 768, need, stream>>>(s2, a);
+        if ((e = cudaFuncSetAttribute(tb_ww, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need_ww)) != cudaSuccess) return e;
+        tb_ww<<<sm_count, 768, need_ww, stream>>>(s2, a);
     } else {
         if ((e = cudaFuncSetAttribute(tb_sm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)need)) != cudaSuccess) return e;
         tb_sm<<<sm_count, 768, need, stream>>>(s2, a);

@@ -23,6 +23,8 @@ struct TbArgs {
     unsigned long long* ticket;  // zeroed before launch
     int2* out;            // pid, dist bits
     uint32_t node_burst, t_leaf, t_pend, t_fin;
+    uint32_t alt;         // tb_ww: 1 = trace_bvh_smem_stack
+    uint32_t sstack_off;  // ... its stack area, in ints from the start of dynamic shared memory
 };
 
 template <int NT>
@@ -41,6 +43,81 @@ __device__ __forceinline__ void tb_stage(const DevScene& sc, SceneView& sv, floa
     sv.sph = s_sph; sv.tri = s_tri; sv.na = s_na; sv.nb = nullptr; sv.nc = nullptr; sv.nd = s_nd;
 }
 
+// Experimental traversal for tb_ww (TbArgs.alt = 1): the product's traversal with the stack in shared memory
+// (entry e of thread t at sstack[e * 768 + t]: conflict-free) instead of local memory.  (alt = 2 was the sphere FILTER
+// inside the node loop: 32.7 ms against 30.8 ms on C3, see profiles/r1_notes.md.)
+constexpr int TB_SSTACK = 24;
+__device__ __forceinline__ void trace_bvh_smem_stack(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr,
+                                                     int* sstack) {
+    best.pid = -1;
+    best.dist = 0.0f;
+    const float BIG = 1e30f;
+    float ix = fminf(fmaxf(__frcp_rn(d.x), -BIG), BIG);
+    float iy = fminf(fmaxf(__frcp_rn(d.y), -BIG), BIG);
+    float iz = fminf(fmaxf(__frcp_rn(d.z), -BIG), BIG);
+    if (!(fabsf(d.x) > 0.0f)) ix = BIG;
+    if (!(fabsf(d.y) > 0.0f)) iy = BIG;
+    if (!(fabsf(d.z) > 0.0f)) iz = BIG;
+    const float ax = fabsf(ix), ay = fabsf(iy), az = fabsf(iz);
+    const float qx = -o.x * ix, qy = -o.y * iy, qz = -o.z * iz;
+    const float slack = 4.8e-7f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 1e-30f;
+    float cull = 1001.0f;
+    int* st = sstack + threadIdx.x;
+    int sp = 0;  // in units of 768 ints
+    int cur = sc.lroot;
+    const int ns = (int)sc.ns;
+    for (uint32_t i = 0; i < sc.nbig; i++) {
+        const int pid = (int)sc.big_pid[i];
+        if (pid < ns) test_sphere<false>(sc, sv.sph[pid], pid, o, d, best, ctr);
+        else if (triangle_filter(sv.tri, pid - ns, o, d, cull)) triangle_exact<false>(sc, sv.tri, pid - ns, pid, o, d, best, ctr);
+        if (best.pid >= 0) cull = fmaf(best.dist, 1.00001f, 1e-6f);
+    }
+    if (!sc.ltree) return;
+    for (;;) {
+        while (cur >= 0) {
+            const float4* nrec = sv.na + 3 * cur;
+            const float4 a = nrec[0], b = nrec[1], c = nrec[2];
+            const int2 ch = sv.nd[cur];
+            const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
+            const float rcx = fmaf(b.z, ix, qx), rcy = fmaf(b.w, iy, qy), rcz = fmaf(c.x, iz, qz);
+            const float tl = fmaxf(fmaxf(fmaf(-a.w, ax, lcx), fmaf(-b.x, ay, lcy)), fmaxf(fmaf(-b.y, az, lcz), 0.0f));
+            const float fl = fminf(fminf(fmaf(a.w, ax, lcx), fmaf(b.x, ay, lcy)), fminf(fmaf(b.y, az, lcz), cull));
+            const float tr = fmaxf(fmaxf(fmaf(-c.y, ax, rcx), fmaf(-c.z, ay, rcy)), fmaxf(fmaf(-c.w, az, rcz), 0.0f));
+            const float fr = fminf(fminf(fmaf(c.y, ax, rcx), fmaf(c.z, ay, rcy)), fminf(fmaf(c.w, az, rcz), cull));
+            const bool hl = tl <= fl + slack;
+            const bool hr = tr <= fr + slack;
+            const bool swap = tr < tl;
+            if (hl && hr) {
+                st[sp] = swap ? ch.x : ch.y;
+                sp += 768;
+            }
+            int nxt = (hr && (!hl || swap)) ? ch.y : ch.x;
+            if (!(hl || hr)) {
+                nxt = TR_DONE;
+                if (sp != 0) {
+                    sp -= 768;
+                    nxt = st[sp];
+                }
+            }
+            cur = nxt;
+        }
+        if (cur == TR_DONE) return;
+        const int first = (~cur) >> 5, count = ((~cur) & 31) + 1;
+        if (first < ns) {
+            for (int i = 0; i < count; i++) test_sphere<false>(sc, sv.sph[first + i], first + i, o, d, best, ctr);
+        } else {
+            for (int i = 0; i < count; i++) {
+                const int pid = first + i;
+                if (triangle_filter(sv.tri, pid - ns, o, d, cull)) triangle_exact<false>(sc, sv.tri, pid - ns, pid, o, d, best, ctr);
+            }
+        }
+        if (best.pid >= 0) cull = fmaf(best.dist, 1.00001f, 1e-6f);
+        if (sp == 0) return;
+        sp -= 768;
+        cur = st[sp];
+    }
+}
+
 __global__ void __launch_bounds__(768, 1) tb_ww(const DevScene sc, const TbArgs a) {
     extern __shared__ float4 smem_dyn[];
     SceneView sv;
@@ -56,7 +133,8 @@ __global__ void __launch_bounds__(768, 1) tb_ww(const DevScene sc, const TbArgs 
         if (i < a.n) {
             const float4 r0 = a.rays[2 * i], r1 = a.rays[2 * i + 1];
             Hit h;
-            trace_bvh_ch<false, true>(sc, sv, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr);  // nbig == 0 skips the list
+            if (a.alt) trace_bvh_smem_stack(sc, sv, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr, a.alt ? reinterpret_cast<int*>(smem_dyn) + a.sstack_off : nullptr);
+            else trace_bvh_ch<false, true>(sc, sv, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr);  // nbig == 0 skips the list
             a.out[i] = make_int2(h.pid, h.pid >= 0 ? __float_as_int(h.dist) : 0);
         }
         __syncwarp();
