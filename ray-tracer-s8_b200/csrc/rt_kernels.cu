@@ -714,8 +714,9 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
     // rounding of the o-term: <= 3 * 2^-24 * |o*inv| per axis, in t (the c- and h-terms are padded on the host)
     const float slack = 4.8e-7f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 1e-30f;
     float cull = 1001.0f;  // a hit has t < T_MAX and length(p-o) ~ t
-    int stack[MAX_STACK];
-    int sp = 0;
+    int stack[MAX_STACK + 1];
+    stack[0] = TR_DONE;  // sentinel: popping it ends the traversal, so a pop needs no emptiness test
+    int sp = 1;
     int cur = sc.lroot;
     const int ns = (int)sc.ns;
     // split layout: the large primitives first (their hits shorten everything that follows)
@@ -749,10 +750,7 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
             const bool swap = tr < tl;
             if (hl && hr) stack[sp++] = swap ? ch.x : ch.y;
             int nxt = (hr && (!hl || swap)) ? ch.y : ch.x;  // the nearer (or the only) child
-            if (!(hl || hr)) {
-                nxt = TR_DONE;
-                if (sp != 0) nxt = stack[--sp];
-            }
+            if (!(hl || hr)) nxt = stack[--sp];
             cur = nxt;
         }
         if (cur == TR_DONE) return;
@@ -768,8 +766,8 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
             }
         }
         if (best.pid >= 0) cull = fmaf(best.dist, 1.00001f, 1e-6f);
-        if (sp == 0) return;
         cur = stack[--sp];
+        if (cur == TR_DONE) return;
     }
 }
 
