@@ -716,7 +716,7 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
     float cull = 1001.0f;  // a hit has t < T_MAX and length(p-o) ~ t
     int stack[MAX_STACK + 1];
     stack[0] = TR_DONE;  // sentinel: popping it ends the traversal, so a pop needs no emptiness test
-    int sp = 1;
+    int* top = stack + 1;  // next free entry
     int cur = sc.lroot;
     const int ns = (int)sc.ns;
     // split layout: the large primitives first (their hits shorten everything that follows)
@@ -748,9 +748,9 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
             if (COUNT) ctr.v[CTR_SLAB] += 2;
             // branch-light step: push and pop are short predicated blocks, the loop has one exit
             const bool swap = tr < tl;
-            if (hl && hr) stack[sp++] = swap ? ch.x : ch.y;
+            if (hl && hr) *top++ = swap ? ch.x : ch.y;
             int nxt = (hr && (!hl || swap)) ? ch.y : ch.x;  // the nearer (or the only) child
-            if (!(hl || hr)) nxt = stack[--sp];
+            if (!(hl || hr)) nxt = *--top;
             cur = nxt;
         }
         if (cur == TR_DONE) return;
@@ -766,7 +766,7 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
             }
         }
         if (best.pid >= 0) cull = fmaf(best.dist, 1.00001f, 1e-6f);
-        cur = stack[--sp];
+        cur = *--top;
         if (cur == TR_DONE) return;
     }
 }
