@@ -344,16 +344,16 @@ def main():
         "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
         "peak_source": "measured live: FFMA-chain micro-benchmark (rt_measure_fp32_peak); MEASURED_PEAKS.json has no CUDA-core figure",
         # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of this
-        # kernel on this workload at 1 GPU (profiles/r1_k2_lanes_final3_ncu_summary.txt); not re-measured live
-        "traffic": (0.905728e6 + 0.752640e6) if (args.workload == "C3" and world == 1) else None,
+        # kernel on this workload at 1 GPU (profiles/r1_k2_lanes_final4_ncu_summary.txt); not re-measured live
+        "traffic": (0.965376e6 + 0.911360e6) if (args.workload == "C3" and world == 1) else None,
         "traffic_unit": "bytes per launch (ncu)",
         "algorithmic_flops_per_launch": flops, "kernel_ms_avg": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
         "flops_per_ray": flops / max(1, cst["rays"]),
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9},
         # pipe / issue view of the same kernel from the committed ncu captures (what the >= 60 % FP32-pipe target is about):
         # K2 on C3 is bound by issue under divergence, K1 (brute force, C2) by the FMA pipe after the f32x2 packing
-        "ncu": ({"source": "profiles/r1_k2_lanes_final3_ncu_summary.txt", "issue_slots_pct": 80.1, "fma_pipe_cycles_pct": 33.1,
-                 "alu_pipe_pct": 62.0, "threads_per_warp_inst": 10.12, "warp_inst": 36.5e9} if cst["intersector_used"] == 2 else
+        "ncu": ({"source": "profiles/r1_k2_lanes_final4_ncu_summary.txt", "issue_slots_pct": 78.4, "fma_pipe_cycles_pct": 34.9,
+                 "alu_pipe_pct": 60.0, "threads_per_warp_inst": 10.49, "warp_inst": 34.4e9} if cst["intersector_used"] == 2 else
                 {"source": "profiles/r1_k1_brute_final_ncu_summary.txt", "issue_slots_pct": 64.3, "fma_pipe_cycles_pct": 60.7,
                  "threads_per_warp_inst": 24.0}) if args.workload in ("C3", "C2") and world == 1 else None,
         "simt_efficiency_query_level": cst["active_lane_iters"] / max(1, cst["total_lane_iters"]),
