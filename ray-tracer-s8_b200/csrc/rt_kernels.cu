@@ -1,20 +1,24 @@
-// rt_kernels.cu — the render megakernel (sm_100a) and its launcher.
+// rt_kernels.cu — the render megakernels (sm_100a) and their launcher.
 //
 // One persistent launch renders a set of 8x4-pixel tiles.  Warps pull tiles from a global ticket
-// counter (dynamic load balance at warp granularity); each lane owns one pixel and runs that pixel's
+// counter (dynamic load balance at warp granularity); a lane owns one pixel at a time and runs that pixel's
 // whole sample/bounce chain from its own xoshiro256++ stream, because the reference draws all of a
 // pixel's samples and bounces sequentially from one generator (ray-tracer-slave/src/main.rs:69-77).
 // The reference's recursion (ray_color, main.rs:108-146) is flattened into ONE loop whose trip is a
 // single nearest-hit query: a lane that finishes a path starts its next sample in the same trip
 // structure, so lanes of a warp stay in the intersection code together regardless of bounce index.
 //
-// Scene geometry (sphere float4s, triangle records, BVH nodes) is staged once per CTA into shared
-// memory when it fits (TEMPLATE SMEM), else read through L1/L2.
+// The product kernel is render_kernel_lanes (lanes are independent workers: a lane that finishes its pixel takes
+// the next pixel of the warp's tile), launched as ONE 768-thread CTA per SM when the scene fits shared memory
+// (geometry + traversal tree staged once per SM, the rest of the 228 KB left to L1 for the traversal stacks) and
+// as 4 x 256 threads at 64 registers when the scene is read through L1/L2.  render_kernel (tile per warp) is the
+// first form, kept for A/B runs together with rt_kernel_sched / _deferred / _wq.cuh and rt_wavefront.cuh.
 //
-//   K1 (ISECT_BRUTE): every primitive per query; a 12-instruction FMA discriminant filter per sphere,
-//                     exact reference arithmetic only for spheres that pass it.
-//   K2 (ISECT_BVH):   ordered, distance-culled traversal of the reference-topology BVH with
-//                     conservative FMA slab tests; exact arithmetic at the leaves.
+//   K1 (ISECT_BRUTE): every primitive per query; the sphere FILTER runs on pairs of spheres in packed f32x2
+//                     arithmetic (FADD2 / FMUL2 / FFMA2), exact reference arithmetic only where it passes.
+//   K2 (ISECT_BVH):   ordered, distance-culled traversal of the traversal tree (big primitives
+//                     first, then a SAH or LBVH tree over the rest) with conservative FMA slab tests in
+//                     centre/half-extent form and a branch-free visit; exact arithmetic at the leaves.
 #include "rt_device.cuh"
 #include "rt_host.h"
 
