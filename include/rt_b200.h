@@ -11,8 +11,9 @@
  *   ImageSlice.image: Vec<u8>           (main.rs:85-90)  →   out_rgb (caller-owned, (h/div)*w*3 bytes)
  *
  * Plain pointers and sizes only; no C++/torch types.  Every call returns RT_OK (0) or a negative
- * rt_status and never throws or unwinds across the boundary (the reference `.unwrap()`s and kills
- * its worker thread instead, main.rs:98,152).  There is no CPU fallback: without a CUDA device
+ * rt_status and never throws or unwinds across the boundary: every entry point catches host exceptions
+ * (RT_ERR_NOMEM / RT_ERR_INTERNAL) (the reference `.unwrap()`s and kills its worker thread instead,
+ * main.rs:98,152).  There is no CPU fallback: without a CUDA device
  * rt_init fails with RT_ERR_NO_DEVICE.
  *
  * Threading: one rt_ctx = one GPU + one stream, single owner, calls serialised by the caller — the
@@ -29,7 +30,7 @@
 extern "C" {
 #endif
 
-#define RT_B200_ABI_VERSION 1
+#define RT_B200_ABI_VERSION 2
 
 typedef enum rt_status {
     RT_OK = 0,
@@ -38,7 +39,10 @@ typedef enum rt_status {
     RT_ERR_NO_DEVICE = -3,     /* no usable CUDA device; there is no CPU fallback */
     RT_ERR_CUDA = -4,          /* CUDA runtime error, text in rt_last_error */
     RT_ERR_BVH = -5,           /* scene the reference's BVH build would panic on (NaN bounds, depth) */
-    RT_ERR_UNSUPPORTED = -6    /* parameter outside this build's limits (e.g. max_bounces > 62) */
+    RT_ERR_UNSUPPORTED = -6,   /* parameter outside this build's limits (e.g. max_bounces > 62) */
+    RT_ERR_NOMEM = -7,         /* host allocation failed */
+    RT_ERR_INTERNAL = -8,      /* an unexpected host exception was caught at the boundary */
+    RT_ERR_TIMEOUT = -9        /* a frame slab never completed (a rank of a multi-GPU frame died) */
 } rt_status;
 
 typedef struct rt_ctx rt_ctx;     /* device, stream, staging buffers */
@@ -86,13 +90,19 @@ typedef struct rt_params {
     float focal_length;    /* 0 → 1    (main.rs:48) */
     uint32_t intersector;  /* rt_intersector */
     uint32_t collect_counters; /* != 0: run the instrumented kernel variant and fill every rt_stats field */
+    uint32_t flags;        /* rt_param_flags: fields whose zero is a value, not "the reference's literal" */
 } rt_params;
+
+typedef enum rt_param_flags {
+    RT_PARAM_MAX_BOUNCES_EXPLICIT = 1, /* max_bounces is taken as given: 0 = camera rays only */
+    RT_PARAM_APERTURE_EXPLICIT = 2     /* aperture is taken as given: 0 = pinhole camera */
+} rt_param_flags;
 
 /* Work counters (for the roofline: SURVEY.md §8d / Appendix C) and timings of the last call. */
 typedef struct rt_stats {
     uint64_t rays;          /* nearest-hit queries = ray_color calls with depth > 0 (always filled) */
     uint64_t primary;       /* camera rays = pixels * spp (always filled) */
-    /* the rest is filled only when params.collect_counters != 0 (instrumented kernel variant) */
+    /* the rest (to total_lane_iters) is filled only when params.collect_counters != 0 (instrumented kernel variant) */
     uint64_t slab_tests;    /* child-box tests during BVH traversal */
     uint64_t sphere_tests;  /* sphere candidate tests (discriminant filter) */
     uint64_t sphere_exact;  /* ... that went through the exact reference arithmetic */
@@ -111,7 +121,9 @@ typedef struct rt_stats {
     uint32_t intersector_used; /* rt_intersector actually run */
     uint32_t kernel_launches;  /* kernels launched by the call */
     uint32_t grid_ctas, cta_threads, ctas_per_sm, scene_in_smem; /* launch shape of the render kernel */
-    uint32_t dyn_smem_bytes, reserved0;
+    uint32_t dyn_smem_bytes;
+    uint32_t redo_pixels;   /* pixels rendered a second time because a query needed the tie-break tables of the scene
+                               (rt_scene_create builds them beside the upload) before they had landed */
 } rt_stats;
 
 /* ---- lifecycle -------------------------------------------------------------------------------- */
@@ -132,8 +144,14 @@ const char* rt_last_error(const rt_ctx* ctx);
 int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles,
                     uint32_t n_triangles, const uint32_t* world_index, rt_scene** out);
 void rt_scene_destroy(rt_ctx* ctx, rt_scene* scene);
+/* rt_scene_create returns as soon as the geometry and the tree the kernels traverse are on the device.  The reference-
+ * topology tree (bvh_impl.rs:229-364), which only decides exact-distance ties and the fate of rays with a zero direction
+ * component, is finished by a builder thread; renders started before it lands are correct all the same (the few pixels
+ * that needed it are rendered again).  This call blocks until it has landed; RT_ERR_BVH if the reference's build would
+ * have panicked on this world. */
+int rt_scene_wait_ready(rt_ctx* ctx, const rt_scene* scene);
 /* BVH facts for tests / tooling: node count (2n-1 like bvh_impl.rs), depth, and the DFS leaf rank of every
- * primitive in world order (rank_out nullable, n entries). */
+ * primitive in world order (rank_out nullable, n entries).  Waits for the builder thread. */
 int rt_scene_info(const rt_scene* scene, uint32_t* n_prims, uint32_t* n_nodes, uint32_t* depth, uint32_t* rank_out);
 /* Bytes rt_scene_create copied host→device for this scene (primitive SoA + BVH nodes + materials). */
 size_t rt_scene_device_bytes(const rt_scene* scene);
@@ -153,12 +171,28 @@ int rt_render_division(rt_ctx* ctx, const rt_scene* scene, const rt_params* para
 int rt_render_frame(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint8_t* out_rgb,
                     size_t out_len, rt_stats* stats);
 
-/* Device-side entry for the multi-GPU tile scheduler: renders the 8x4-pixel tiles t of the whole frame
- * with (t % tile_ranks) == tile_rank into a full-frame DEVICE buffer `frame_dev` (height*width*3 bytes;
+/* One frame on n GPUs from ONE process (the controller's fan-out, ray-tracer-controller/src/main.rs:47-75,109-119,
+ * without HTTP): ctxs[i] renders the tiles t with t % n == (i + t / n) % n — the interleave of rt_render_tiles_device —
+ * of the scene scenes[i] (the same world, created on ctxs[i]) straight into a frame in ctxs[0]'s memory over peer
+ * access (NVLink stores), and finished slabs of the frame stream to out_rgb (host, height*width*3 bytes) while the rest
+ * still renders.  Contexts may share a device.  stats (nullable): counters summed over the contexts, kernel_ms the
+ * slowest context's.  params->division_no is ignored. */
+int rt_render_frame_multi(rt_ctx* const* ctxs, const rt_scene* const* scenes, uint32_t n, const rt_params* params,
+                          uint8_t* out_rgb, size_t out_len, rt_stats* stats);
+
+/* Device-side entry for the multi-GPU tile scheduler: renders the 8x4-pixel tiles of the whole frame that belong to
+ * rank tile_rank of tile_ranks (tile t, row-major over the tile grid, belongs to rank (t % ranks - t / ranks) mod ranks:
+ * a rotating interleave) into a full-frame DEVICE buffer `frame_dev` (height*width*3 bytes;
  * may be a peer-mapped pointer into another GPU's memory, in which case the stores travel over NVLink).
  * Asynchronous on the ctx stream unless `sync` != 0. stats (nullable) is filled only when sync != 0. */
 int rt_render_tiles_device(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint32_t tile_rank,
                            uint32_t tile_ranks, void* frame_dev, int sync, rt_stats* stats);
+/* The frame owner's form of the call above: renders this context's tiles into frame_dev (allocated by this context with
+ * rt_frame_alloc) and, while they render, copies every slab of frame number `seq` to out_rgb as soon as ALL ranks have
+ * finished it (see rt_frame_collect).  Returns with the complete frame in out_rgb (height*width*3 bytes). */
+int rt_render_tiles_collect(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint32_t tile_rank,
+                            uint32_t tile_ranks, void* frame_dev, uint64_t seq, uint8_t* out_rgb, size_t out_len,
+                            rt_stats* stats);
 int rt_sync(rt_ctx* ctx);
 /* The ctx stream as a cudaStream_t, for callers that order their own work (NCCL, copies) after a render. */
 void* rt_stream(rt_ctx* ctx);
@@ -175,17 +209,23 @@ int rt_frame_open(rt_ctx* ctx, const uint8_t handle[64], void** dev_out);
 int rt_frame_close(rt_ctx* ctx, void* dev);
 int rt_frame_free(rt_ctx* ctx, void* dev);
 int rt_frame_download(rt_ctx* ctx, const void* frame_dev, uint8_t* out_rgb, size_t bytes);
+/* Every frame from rt_frame_alloc carries a control block: the render kernels of all ranks add the pixels they finish
+ * to per-slab counters in it (system-scope releases, also over NVLink).  On the frame's owner: wait until frame number
+ * `seq` (1 = the first frame rendered into this buffer; counters are cumulative, the frame size must not change) is
+ * complete — no barrier between the ranks is needed — and, if out_rgb is not NULL, copy each slab to the host as soon
+ * as it is complete, while other slabs still render.  RT_ERR_TIMEOUT if a slab does not complete within 20 s. */
+int rt_frame_collect(rt_ctx* ctx, const void* frame_dev, const rt_params* params, uint64_t seq, uint8_t* out_rgb,
+                     size_t out_len);
+/* Flow control for ranks that do not own the frame: everything queued on this context's stream after this call (the
+ * next rt_render_tiles_device into frame_dev) waits, on the device, until the owner has finished collecting frame
+ * number `seq` of the buffer (rt_frame_collect / rt_render_tiles_collect mark it).  seq == 0 is a no-op.  A rank that
+ * renders frame k of a buffer calls this with k - 1; with two buffers used alternately ranks run a frame ahead. */
+int rt_frame_wait_consumed(rt_ctx* ctx, const void* frame_dev, size_t frame_bytes, uint64_t seq);
 
 /* ---- measurement helpers --------------------------------------------------------------------------- */
 /* FFMA-chain micro-benchmark: achieved FP32 TFLOP/s (2 flops per FFMA) on this device, for the
  * roofline denominator (MEASURED_PEAKS.json has no CUDA-core figure). */
 int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops_out, float* ms_out);
-/* Trace-only benchmark (development aid, csrc/rt_trace_bench.cuh; with_big 2 / 3 = 0 / 1 on rays sorted by octant + cell): renders one frame while recording up to max_rays of
- * its nearest-hit queries, then times the query alone over the recorded rays as (a) the product kernel's while-while
- * traversal and (b) a ballot-scheduled state machine with dynamic fetch, and counts rays whose answers differ.
- * with_big = 0 leaves the split layout's big primitives out of both.  The scene must fit shared memory. */
-int rt_debug_trace_bench(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint64_t max_rays, int with_big,
-                         uint64_t* n_rays_out, float* ms_while_while, float* ms_state_machine, uint64_t* mismatches_out);
 /* Device properties: sm_count, clock_khz (max SM clock), smem_optin bytes. Nullable outputs. */
 int rt_device_info(rt_ctx* ctx, int* sm_count, int* clock_khz, int* smem_optin, char name_out[64]);
 

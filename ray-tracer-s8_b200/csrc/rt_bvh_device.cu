@@ -164,6 +164,8 @@ size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
 }  // namespace
 
+#ifdef RT_B200_EXPERIMENTS
+
 // ---- measurement aid for rt_debug_trace_bench: reorder recorded rays by (direction octant, origin cell) -----------
 namespace {
 __global__ void ray_keys(const float4* __restrict__ rays, unsigned long long n, float3 lo, float3 scale,
@@ -217,6 +219,8 @@ cudaError_t sort_rays_device(const float4* rays, unsigned long long n, const flo
     return e;
 }
 
+#endif  // RT_B200_EXPERIMENTS
+
 void free_device_build(DeviceBuild* b) {
     if (b->mem) cudaFree(b->mem);
     *b = DeviceBuild();
@@ -262,7 +266,7 @@ cudaError_t build_lbvh_device(DeviceBuild* buf, const float* h_boxes, const uint
         if ((e = cudaMalloc(&buf->mem, cap)) != cudaSuccess) return e;
         buf->bytes = cap;
     }
-    static const bool timing = std::getenv("RT_B200_TIMING") != nullptr;
+    const bool timing = tunables().timing;
     if (timing) fprintf(stderr, "[build_lbvh_device n=%u] scratch %zu bytes of %zu\n", n, off, buf->bytes);
     uint8_t* m = (uint8_t*)buf->mem;
     float* d_boxes = (float*)(m + o_box);

@@ -28,21 +28,16 @@ constexpr float T_MAX = 1000.0f; // shapes/mod.rs:13
 // < 0 leaf with pid = ~code.
 // ---------------------------------------------------------------------------------------------
 struct DevScene {
+    // The first four arrays are adjacent in the scene blob, in this order, each a multiple of 16 bytes:
+    //   sph | tri | lnode_a | lnode_d          (the shared-memory image of the BVH kernel: ONE bulk copy per CTA)
     const float4* sph;     // [ns]    cx, cy, cz, r*r
     const float4* tri;     // [nt*4]  a | b-a | c-a | normalize_or_zero((a-b)x(a-c))
+    // the traversal tree: one 48-byte record per inner node (two child boxes in centre/half-extent form, padded
+    // for FILTER rounding) and the child codes: >= 0 inner node index, < 0 leaf ~((first_pid << 5) | (count-1))
+    const float4* lnode_a;  // [lni*3] a | b | c: l.c.xyz, l.h.x | l.h.yz, r.c.xy | r.c.z, r.h.xyz
+    const int2* lnode_d;    // [lni]
     const float4* sph2;    // [ceil8(ns)] sphere pairs for the packed f32x2 filter: -c.x pair, -c.y pair | -c.z pair, r*r pair
-    const float4* node_a;  // [ni]    l.min.xyz, l.max.x
-    const float4* node_b;  // [ni]    l.max.yz,  r.min.xy
-    const float4* node_c;  // [ni]    r.min.z,   r.max.xyz
-    const int2* node_d;    // [ni]    left code, right code
-    const float4* cnode_a; // [ni]    centre/half-extent form of the same boxes (scheduled kernel):
-    const float4* cnode_b; //         l.c.xyz, l.h.x | l.h.yz, r.c.xy | r.c.z, r.h.xyz
-    const float4* cnode_c;
-    // the same tree with every subtree of <= L same-kind primitives collapsed into one leaf (lanes kernel):
-    // pids are in DFS order, so a subtree is a contiguous pid range; leaf code = ~((first_pid << 5) | (count-1))
-    const float4* lnode_a;  // [lni*3] one 48-byte record per node (a | b | c): a single address per visit
-    const int2* lnode_d;
-    uint32_t lni;          // inner nodes of the collapsed tree
+    uint32_t lni;          // inner nodes of the traversal tree
     int lroot;             // its root code
     // "split" traversal layout: the few primitives whose box is a large share of the scene's (a ground plane's two
     // triangles) are kept out of the tree and tested first, so they neither inflate the upper boxes nor cost node
@@ -52,11 +47,29 @@ struct DevScene {
     uint32_t big_pid[MAX_BIG];
     const float4* mat;     // [ns+nt] albedo rgb, roughness
     const float* emis;     // [ns+nt]
-    const uint32_t* rank;  // [ns+nt] DFS leaf rank (exact-distance tie-break, shapes/mod.rs:177-182)
+    const uint32_t* rank;  // [ns+nt] DFS leaf rank in the REFERENCE tree (exact-distance tie-break, shapes/mod.rs:177-182)
     const float4* leaf_box;  // [(ns+nt)*2] the shape's own AABB exactly as the reference computes it (min | max)
-    uint32_t ns, nt, ni;
+    // the reference tree's ancestor chain, walked only by rays with a zero direction component (NaN / inf slabs,
+    // ray.rs:82-112,174-194): up[pid] / up[n + node] = (parent inner node << 1) | side, UP_ROOT at the root;
+    // ref_box[2*(2*node + side)] = that child's box (min | max), unpadded
+    const uint32_t* ref_up;
+    const float4* ref_box;
+    int aux_ready;         // rank / ref_up / ref_box have landed (they are built beside the upload, rt_scene.cu); while 0,
+                           // a query that needs them marks its pixel for a second pass instead
+    uint32_t ns, nt, ni;   // ni = inner nodes of the reference tree
+#ifdef RT_B200_EXPERIMENTS
+    // the reference-topology tree in the first kernels' formats (A/B kernels under csrc/experiments/ only)
+    const float4* node_a;  // [ni]    l.min.xyz, l.max.x
+    const float4* node_b;  // [ni]    l.max.yz,  r.min.xy
+    const float4* node_c;  // [ni]    r.min.z,   r.max.xyz
+    const int2* node_d;    // [ni]    left code, right code
+    const float4* cnode_a; // [ni]    centre/half-extent form of the same boxes:
+    const float4* cnode_b; //         l.c.xyz, l.h.x | l.h.yz, r.c.xy | r.c.z, r.h.xyz
+    const float4* cnode_c;
     int root;              // child code of the root
+#endif
 };
+constexpr uint32_t UP_ROOT = 0xffffffffu;
 
 struct DevCamera {            // Camera::new (camera.rs:19-47), evaluated on the host in reference order
     float org[3], llc[3], hor[3], ver[3];
@@ -71,20 +84,40 @@ struct DevParams {
     uint32_t spp, depth;         // depth = max_bounces + 1 nearest-hit queries per sample at most
     uint64_t seed;
     uint32_t tile_rank, tile_ranks;
-    uint8_t* out;                // RGB8; buffer row 0 = global row out_row0
+    uint8_t* out;                // RGB8; buffer row 0 = global row out_row0 (may be a peer-mapped frame: stores travel over NVLink)
     uint32_t out_row0;
     uint32_t tiles_x, tiles_y;
-    unsigned int* tile_counter;  // zeroed before launch
+    // work hand-out: tickets [0, tail_first) are whole 8x4 tiles pulled by warps; tickets [tail_first, my_tickets) are
+    // handed out pixel by pixel to single lanes, so the last few per cent of the launch keep every lane busy
+    unsigned int* tile_counter;  // [0] tile tickets, [1] pixel tickets of the tail; zeroed before launch
+    uint32_t my_tickets, tail_first;
+    int tile_order_reverse;      // 1: tickets walk the tile grid from the last tile to the first
+    // completion counting (nullable): done[slab] += pixels written, slab = tile row / slab_tile_rows; released
+    // with a system-scope fence so the frame owner may copy a slab out as soon as its count is complete
+    unsigned long long* done;
+    uint32_t slab_tile_rows;
     unsigned long long* counters;  // NUM_COUNTERS
+    // second pass (rt_api.cu finish_redo): pixels whose queries needed the tie-break tables before they had landed are
+    // appended to redo_list (y * width + x; *redo_count may exceed the capacity: then the whole launch is repeated);
+    // a launch with pixel_list != nullptr renders exactly those pixels, from pixel tickets only
+    unsigned int* redo_list;
+    unsigned long long* redo_count;
+    uint32_t redo_cap;
+    // defer_redo != 0 (a non-owner rank of a shared frame): such a pixel is NOT added to `done` now but by the second
+    // pass, so a slab the frame owner sees complete is final; redo_slab[slab] counts them (for the case the list overflows)
+    int defer_redo;
+    unsigned long long* redo_slab;
+    const unsigned int* pixel_list;
+    uint32_t list_count;
+#ifdef RT_B200_EXPERIMENTS
     // scheduled kernels: pool weights (NODE, LEAF, HIT, PRIM) and the NODE phase's stay-in-loop share num/den
     int sched_w[4];
     int sched_node_num, sched_node_den;
-    int tile_order_reverse;      // 1: tickets walk the tile grid from the last tile to the first
-    int list_max_prims;          // primary-ray candidate lists are built when the scene has at most this many primitives
     // measurement aid (COUNT instantiation only): every query's ray is appended here (rt_trace_bench.cuh)
     float4* ray_dump;
     unsigned long long* ray_dump_n;
     unsigned long long ray_dump_cap;
+#endif
 };
 
 enum CounterSlot {

@@ -1,4 +1,4 @@
-// rt_host.h — host-side declarations shared by rt_api.cu, rt_kernels.cu and rt_bvh_host.cpp.
+// rt_host.h — host-side declarations shared by rt_api.cu, rt_scene.cu, rt_multi.cu, rt_kernels.cu and rt_bvh_host.cpp.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -14,14 +14,60 @@ struct DevScene;
 struct DevCamera;
 struct DevParams;
 
+constexpr int MAX_SLABS = 64;  // completion counters per frame (frame control block)
+
+// Measurement switches, read from the environment once per process (rt_init forces the read).  Not API.
+struct Tunables {
+    int smem_override = -1;      // RT_B200_SMEM=0|1: force the scene out of / into shared memory
+    int tile_order_reverse = 1;  // RT_B200_TILE_ORDER=topdown: tickets walk the tile grid top-down
+    bool stage_out = true;       // RT_B200_STAGE_OUT=0: finished pixels go to the frame as byte stores
+    int tail_permille = 30;      // RT_B200_TAIL_PERMILLE: share of the tickets handed out pixel by pixel
+    int build_mode = 1;          // RT_B200_BUILD=host|device|auto: who builds the traversal tree
+    int tree_mode = 2;           // RT_B200_TREE=ref|sah|split: which tree is traversed
+    bool timing = false;         // RT_B200_TIMING: stage times of rt_scene_create on stderr
+    int slabs = 16;              // RT_B200_SLABS: slabs a frame download is streamed in
+    bool async_ref = true;       // RT_B200_ASYNC_REF=0: build the reference-topology tree inside rt_scene_create
+#ifdef RT_B200_EXPERIMENTS
+    int bvh_variant = 3;         // RT_B200_BVH_KERNEL=lanes|simple|pools|deferred|wave|wq
+    int sched_minb = 2;
+    int w[4] = {1, 1, 1, 1}, node_num = 1, node_den = 2;
+    int wave_refill = 8;
+    int wq_warps = 24, wq_chains = 128, wq_min_active = 20, wq_min_node = 24, wq_burst = 2, wq_t_leaf = 4, wq_t_pend = 6,
+        wq_t_fin = 6, wq_sync = 0, wq_budget = 0, tb_alt = 0, tb_burst = 4;
+#endif
+};
+const Tunables& tunables();
+
 struct LaunchInfo {
     unsigned grid = 0, threads = 0;
     size_t dyn_smem = 0;
     int ctas_per_sm = 0;
     bool scene_in_smem = false;
     unsigned launches = 1;
+    bool counts_done = true;  // the kernel keeps the frame's completion counters (the A/B kernels do not)
 };
 
+// rt_bvh_device.cu: LBVH + refit of the traversal tree on the device (scratch owned by the context)
+struct DeviceBuild {
+    void* mem = nullptr;
+    size_t bytes = 0;
+};
+void free_device_build(DeviceBuild* b);
+cudaError_t build_lbvh_device(DeviceBuild* buf, const float* h_boxes, const uint32_t* h_pid_of, uint32_t n,
+                              float4* lnode_abc, int2* lnode_d, uint32_t* depth_out, cudaStream_t stream);
+
+// rt_kernels.cu
+cudaError_t preload_kernels();
+cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevParams& pr, int isect, bool count,
+                          int sm_count, int smem_optin, cudaStream_t stream, LaunchInfo* info);
+cudaError_t launch_wait_slab(const unsigned long long* done, unsigned long long target, unsigned int* timeout_flag,
+                             cudaStream_t stream);
+cudaError_t launch_set_u64(unsigned long long* p, unsigned long long v, cudaStream_t stream);
+cudaError_t launch_add_counts(unsigned long long* done, const unsigned long long* add, int n, cudaStream_t stream);
+cudaError_t launch_fp32_peak(float* scratch, int sm_count, int iters, cudaStream_t stream);
+size_t scene_smem_bytes(const DevScene& sc, int isect);
+
+#ifdef RT_B200_EXPERIMENTS
 // device buffers of the wavefront pipeline (owned by the context, grown on demand)
 struct WaveBuffers {
     void* slots = nullptr;          // WSlot[capacity]
@@ -33,40 +79,24 @@ struct WaveBuffers {
     size_t capacity = 0, ext_entries = 0;
 };
 void free_wave_buffers(WaveBuffers* wb);
-
 // device buffer of the warp-private wavefront kernel: per-chain state (rt_kernel_wq.cuh), grown on demand
 struct WqBuffers {
     void* state = nullptr;
     size_t bytes = 0;
 };
 void free_wq_buffers(WqBuffers* b);
-bool use_wq(int isect, const DevParams& pr);
-cudaError_t launch_wq(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
-                      int smem_optin, cudaStream_t stream, WqBuffers* wb, LaunchInfo* info);
-
-// rt_bvh_device.cu: LBVH + refit of the traversal tree on the device (scratch owned by the context)
-struct DeviceBuild {
-    void* mem = nullptr;
-    size_t bytes = 0;
+struct ExperimentBuffers {
+    WaveBuffers wave;
+    WqBuffers wq;
 };
-void free_device_build(DeviceBuild* b);
-cudaError_t build_lbvh_device(DeviceBuild* buf, const float* h_boxes, const uint32_t* h_pid_of, uint32_t n,
-                              float4* lnode_abc, int2* lnode_d, uint32_t* depth_out, cudaStream_t stream);
-
-cudaError_t sort_rays_device(const float4* rays, unsigned long long n, const float lo[3], const float hi[3], float4* out,
-                             cudaStream_t stream);
-
-// rt_kernels.cu
-cudaError_t launch_wavefront(const DevScene& sc, const DevCamera& cam, const DevParams& pr, bool count, int sm_count,
-                             int smem_optin, cudaStream_t stream, WaveBuffers* wb, LaunchInfo* info);
-bool use_wavefront(int isect);
+void set_experiment_buffers(ExperimentBuffers* b);  // the context whose launch follows (single-threaded tooling)
+void free_experiment_buffers(ExperimentBuffers* b);
 bool legacy_node_arrays_needed();  // true when RT_B200_BVH_KERNEL selects a kernel that reads node_* / cnode_*
-cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevParams& pr, int isect, bool count,
-                          int sm_count, int smem_optin, cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_trace_bench(const DevScene& sc, int variant, bool with_big, const float4* rays, unsigned long long n,
                                unsigned long long* ticket, int2* out, int sm_count, int smem_optin, cudaStream_t stream);
-cudaError_t launch_fp32_peak(float* scratch, int sm_count, int iters, cudaStream_t stream);
-size_t scene_smem_bytes(const DevScene& sc, int isect);
+cudaError_t sort_rays_device(const float4* rays, unsigned long long n, const float lo[3], const float hi[3], float4* out,
+                             cudaStream_t stream);
+#endif
 
 // ---- rt_bvh_host.cpp: SAH BVH with the reference's topology ------------------------------------------
 struct Box {

@@ -9,7 +9,10 @@ import ctypes as C
 import os
 
 PKG_DIR = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.normpath(os.path.join(PKG_DIR, "..", "lib", "librt_b200.so"))
+LIB_DIR = os.path.normpath(os.path.join(PKG_DIR, "..", "lib"))
+# RT_B200_LIB=exp selects the experiments build (product + the A/B kernels of csrc/experiments/, `make exp`): tooling and
+# the variant-agreement test only.  The product library is the default and carries no A/B code.
+LIB_PATH = os.path.join(LIB_DIR, "librt_b200_exp.so" if os.environ.get("RT_B200_LIB") == "exp" else "librt_b200.so")
 
 RT_OK = 0
 RT_ERR_INVALID_ARG = -1
@@ -18,10 +21,14 @@ RT_ERR_NO_DEVICE = -3
 RT_ERR_CUDA = -4
 RT_ERR_BVH = -5
 RT_ERR_UNSUPPORTED = -6
+RT_ERR_NOMEM = -7
+RT_ERR_INTERNAL = -8
+RT_ERR_TIMEOUT = -9
 STATUS_NAMES = {
     0: "RT_OK", -1: "RT_ERR_INVALID_ARG", -2: "RT_ERR_EMPTY_SCENE", -3: "RT_ERR_NO_DEVICE", -4: "RT_ERR_CUDA",
-    -5: "RT_ERR_BVH", -6: "RT_ERR_UNSUPPORTED",
+    -5: "RT_ERR_BVH", -6: "RT_ERR_UNSUPPORTED", -7: "RT_ERR_NOMEM", -8: "RT_ERR_INTERNAL", -9: "RT_ERR_TIMEOUT",
 }
+PARAM_MAX_BOUNCES_EXPLICIT, PARAM_APERTURE_EXPLICIT = 1, 2
 
 INTERSECT_AUTO, INTERSECT_BRUTE, INTERSECT_BVH = 0, 1, 2
 
@@ -33,7 +40,7 @@ class RtParams(C.Structure):
         ("cam_origin", C.c_float * 3),
         ("aperture", C.c_float), ("focus_distance", C.c_float), ("field_of_view", C.c_float),
         ("focal_length", C.c_float),
-        ("intersector", C.c_uint32), ("collect_counters", C.c_uint32),
+        ("intersector", C.c_uint32), ("collect_counters", C.c_uint32), ("flags", C.c_uint32),
     ]
 
 
@@ -47,7 +54,7 @@ class RtStats(C.Structure):
         ("kernel_ms", C.c_float), ("total_ms", C.c_float),
         ("intersector_used", C.c_uint32), ("kernel_launches", C.c_uint32),
         ("grid_ctas", C.c_uint32), ("cta_threads", C.c_uint32), ("ctas_per_sm", C.c_uint32),
-        ("scene_in_smem", C.c_uint32), ("dyn_smem_bytes", C.c_uint32), ("reserved0", C.c_uint32),
+        ("scene_in_smem", C.c_uint32), ("dyn_smem_bytes", C.c_uint32), ("redo_pixels", C.c_uint32),
     ]
 
     def as_dict(self):
@@ -64,8 +71,10 @@ EXPORTS = [
     "rt_scene_info", "rt_render_division", "rt_render_frame", "rt_render_tiles_device", "rt_sync", "rt_stream",
     "rt_host_alloc", "rt_host_free", "rt_frame_alloc", "rt_frame_open", "rt_frame_close", "rt_frame_free",
     "rt_frame_download", "rt_measure_fp32_peak", "rt_device_info", "rt_bvh_build_host", "rt_struct_sizes", "rt_scene_device_bytes",
-    "rt_debug_trace_bench",
+    "rt_scene_wait_ready", "rt_render_frame_multi", "rt_frame_collect", "rt_render_tiles_collect", "rt_frame_wait_consumed",
 ]
+# only in the experiments build (csrc/experiments/rt_experiments_api.h)
+EXPERIMENT_EXPORTS = ["rt_debug_trace_bench"]
 
 _lib = None
 
@@ -126,9 +135,20 @@ def lib():
     L.rt_frame_download.restype = i32
     L.rt_measure_fp32_peak.argtypes = [vp, C.POINTER(C.c_double), C.POINTER(C.c_float)]
     L.rt_measure_fp32_peak.restype = i32
-    L.rt_debug_trace_bench.argtypes = [vp, vp, C.c_void_p, C.c_uint64, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_float),
-                                       C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
-    L.rt_debug_trace_bench.restype = i32
+    if hasattr(L, "rt_debug_trace_bench"):
+        L.rt_debug_trace_bench.argtypes = [vp, vp, C.c_void_p, C.c_uint64, i32, C.POINTER(C.c_uint64), C.POINTER(C.c_float),
+                                           C.POINTER(C.c_float), C.POINTER(C.c_uint64)]
+        L.rt_debug_trace_bench.restype = i32
+    L.rt_scene_wait_ready.argtypes = [vp, vp]
+    L.rt_scene_wait_ready.restype = i32
+    L.rt_render_frame_multi.argtypes = [pp, pp, u32, C.POINTER(RtParams), vp, sz, C.POINTER(RtStats)]
+    L.rt_render_frame_multi.restype = i32
+    L.rt_render_tiles_collect.argtypes = [vp, vp, C.POINTER(RtParams), u32, u32, vp, C.c_uint64, vp, sz, C.POINTER(RtStats)]
+    L.rt_render_tiles_collect.restype = i32
+    L.rt_frame_wait_consumed.argtypes = [vp, vp, sz, C.c_uint64]
+    L.rt_frame_wait_consumed.restype = i32
+    L.rt_frame_collect.argtypes = [vp, vp, C.POINTER(RtParams), C.c_uint64, vp, sz]
+    L.rt_frame_collect.restype = i32
     L.rt_device_info.argtypes = [vp, C.POINTER(i32), C.POINTER(i32), C.POINTER(i32), C.c_char_p]
     L.rt_device_info.restype = i32
     L.rt_bvh_build_host.argtypes = [vp, u32, vp, u32, vp, vp, C.POINTER(u32), C.POINTER(u32)]

@@ -25,9 +25,12 @@ class RtError(RuntimeError):
 
 def make_params(width, height, divisions=1, division_no=0, spp=0, max_bounces=0, seed=0,
                 cam_origin=(0.0, 0.0, 0.0), aperture=0.0, focus_distance=0.0, field_of_view=0.0,
-                focal_length=0.0, intersector=INTERSECT_AUTO, collect_counters=False) -> RtParams:
-    """Zero fields mean the reference's literals (spp 100, max_bounces 10, aperture 0.1, ...)."""
+                focal_length=0.0, intersector=INTERSECT_AUTO, collect_counters=False, explicit=()) -> RtParams:
+    """Zero fields mean the reference's literals (spp 100, max_bounces 10, aperture 0.1, ...), except the fields named
+    in `explicit` ("max_bounces": 0 = camera rays only; "aperture": 0 = pinhole), whose zero is taken as given."""
     p = RtParams()
+    p.flags = ((_abi.PARAM_MAX_BOUNCES_EXPLICIT if "max_bounces" in explicit else 0)
+               | (_abi.PARAM_APERTURE_EXPLICIT if "aperture" in explicit else 0))
     p.width, p.height, p.divisions, p.division_no = width, height, divisions, division_no
     p.spp, p.max_bounces, p.seed = spp, max_bounces, seed
     p.cam_origin[:] = [float(c) for c in cam_origin]
@@ -74,6 +77,9 @@ class Context:
 
     def close(self):
         if getattr(self, "_h", None):
+            for p in getattr(self, "_pinned", []):
+                self._lib.rt_host_free(self._h, p)
+            self._pinned = []
             self._lib.rt_shutdown(self._h)
             self._h = None
 
@@ -101,7 +107,10 @@ class Context:
         return tf.value, ms.value
 
     def trace_bench(self, scene: "Scene", params: RtParams, max_rays: int, with_big: bool = True, sort: bool = False):
-        """Development aid: the nearest-hit query alone over the recorded queries of one frame (rt_trace_bench.cuh)."""
+        """Development aid (experiments build, RT_B200_LIB=exp): the nearest-hit query alone over the recorded queries of
+        one frame (csrc/experiments/rt_trace_bench.cuh)."""
+        if not hasattr(self._lib, "rt_debug_trace_bench"):
+            raise RtError(_abi.RT_ERR_UNSUPPORTED, "rt_debug_trace_bench exists only in librt_b200_exp.so (RT_B200_LIB=exp)")
         n, bad = C.c_uint64(), C.c_uint64()
         ms_ww, ms_sm = C.c_float(), C.c_float()
         self._check(self._lib.rt_debug_trace_bench(self._h, scene._h, C.byref(params), int(max_rays), (1 if with_big else 0) + (2 if sort else 0),
@@ -132,14 +141,22 @@ class Context:
         return arr
 
     # -- render -----------------------------------------------------------------------------------
+    @staticmethod
+    def _out_buffer(out, shape):
+        """A caller-supplied destination must be exactly the bytes the library will write."""
+        if out is None:
+            return np.empty(shape, dtype=np.uint8)
+        if not isinstance(out, np.ndarray) or out.dtype != np.uint8 or not out.flags["C_CONTIGUOUS"] or not out.flags["WRITEABLE"]:
+            raise RtError(_abi.RT_ERR_INVALID_ARG, "out must be a writable C-contiguous uint8 numpy array")
+        return out
+
     def render_division(self, scene: "Scene", params: RtParams, out: np.ndarray | None = None, want_stats=False):
         """Band `params.division_no` → uint8 (height/divisions, width, 3); row 0 = top of the band."""
         div = params.divisions or 1
         if params.height % div != 0:
             raise RtError(_abi.RT_ERR_INVALID_ARG, f"height {params.height} is not a multiple of divisions {div}")
         rows = params.height // div
-        if out is None:
-            out = np.empty((rows, params.width, 3), dtype=np.uint8)
+        out = self._out_buffer(out, (rows, params.width, 3))
         st = RtStats()
         self._check(self._lib.rt_render_division(self._h, scene._h, C.byref(params), out.ctypes.data_as(C.c_void_p),
                                                  out.nbytes, C.byref(st)))
@@ -147,8 +164,7 @@ class Context:
 
     def render_frame(self, scene: "Scene", params: RtParams, out: np.ndarray | None = None, want_stats=False):
         """All divisions in one launch → uint8 (height, width, 3)."""
-        if out is None:
-            out = np.empty((params.height, params.width, 3), dtype=np.uint8)
+        out = self._out_buffer(out, (params.height, params.width, 3))
         st = RtStats()
         self._check(self._lib.rt_render_frame(self._h, scene._h, C.byref(params), out.ctypes.data_as(C.c_void_p),
                                               out.nbytes, C.byref(st)))
@@ -160,6 +176,17 @@ class Context:
         st = RtStats()
         self._check(self._lib.rt_render_tiles_device(self._h, scene._h, C.byref(params), tile_rank, tile_ranks,
                                                      C.c_void_p(frame_dev), 1 if sync else 0, C.byref(st)))
+        return st.as_dict() if want_stats else None
+
+    def render_tiles_collect(self, scene: "Scene", params: RtParams, tile_rank: int, tile_ranks: int, frame_dev: int,
+                             seq: int, out: np.ndarray, want_stats=False):
+        """Frame owner: this rank's tiles into its frame, and the whole frame (all ranks' slabs, as they complete) into
+        `out` while they render."""
+        out = self._out_buffer(out, None)
+        st = RtStats()
+        self._check(self._lib.rt_render_tiles_collect(self._h, scene._h, C.byref(params), tile_rank, tile_ranks,
+                                                      C.c_void_p(frame_dev), int(seq), out.ctypes.data_as(C.c_void_p),
+                                                      out.nbytes, C.byref(st)))
         return st.as_dict() if want_stats else None
 
     # -- shared frame (one NVLink box, one process per GPU) ----------------------------------------------
@@ -182,8 +209,38 @@ class Context:
         self._check(self._lib.rt_frame_free(self._h, C.c_void_p(dev)))
 
     def frame_download(self, dev: int, out: np.ndarray):
+        out = self._out_buffer(out, None)
         self._check(self._lib.rt_frame_download(self._h, C.c_void_p(dev), out.ctypes.data_as(C.c_void_p), out.nbytes))
         return out
+
+    def frame_wait_consumed(self, dev: int, nbytes: int, seq: int):
+        """Non-owner rank: later work on this context's stream waits until the owner has collected frame `seq`."""
+        self._check(self._lib.rt_frame_wait_consumed(self._h, C.c_void_p(dev), nbytes, int(seq)))
+
+    def frame_collect(self, dev: int, params: RtParams, seq: int, out: np.ndarray | None = None):
+        """Frame owner: wait (on the device) until frame number `seq` of the buffer is complete — every rank's kernel
+        counts the pixels it finishes in the frame's control block — and stream finished slabs into `out` meanwhile."""
+        if out is not None:
+            out = self._out_buffer(out, None)
+        self._check(self._lib.rt_frame_collect(self._h, C.c_void_p(dev), C.byref(params), int(seq),
+                                               None if out is None else out.ctypes.data_as(C.c_void_p),
+                                               0 if out is None else out.nbytes))
+        return out
+
+
+def render_frame_multi(ctxs, scenes, params: RtParams, out: np.ndarray | None = None, want_stats=False):
+    """One frame on several GPUs from this process (rt_render_frame_multi): context i renders rank i's tiles of its own
+    copy of the scene straight into context 0's frame over peer access; finished slabs stream to `out`."""
+    if len(ctxs) != len(scenes) or not ctxs:
+        raise RtError(_abi.RT_ERR_INVALID_ARG, "one scene per context")
+    out = Context._out_buffer(out, (params.height, params.width, 3))
+    n = len(ctxs)
+    ch = (C.c_void_p * n)(*[c._h for c in ctxs])
+    sh = (C.c_void_p * n)(*[s._h for s in scenes])
+    st = RtStats()
+    ctxs[0]._check(ctxs[0]._lib.rt_render_frame_multi(ch, sh, n, C.byref(params), out.ctypes.data_as(C.c_void_p),
+                                                      out.nbytes, C.byref(st)))
+    return (out, st.as_dict()) if want_stats else out
 
 
 class Scene:
@@ -207,6 +264,11 @@ class Scene:
         rank = np.zeros(self.n_spheres + self.n_triangles, dtype=np.uint32)
         self._ctx._check(self._ctx._lib.rt_scene_info(self._h, C.byref(n), C.byref(nn), C.byref(d), _ptr(rank)))
         return {"n_prims": n.value, "n_nodes": nn.value, "depth": d.value, "rank": rank}
+
+    def wait_ready(self):
+        """Block until the tie-break tables (reference-topology tree, built beside the upload) are on the device."""
+        self._ctx._check(self._ctx._lib.rt_scene_wait_ready(self._ctx._h, self._h))
+        return self
 
     @property
     def device_bytes(self) -> int:

@@ -132,7 +132,8 @@ def test_large_scene_l2_resident_path(ctx, rt, O):
 
 
 def test_kernel_variants_agree(rt, O):
-    """The alternative pipelines kept for A/B measurements (RT_B200_BVH_KERNEL) render the same bytes.
+    """The alternative pipelines kept for A/B measurements (RT_B200_BVH_KERNEL; experiments build of the library,
+    lib/librt_b200_exp.so, which is NOT what the product loads) render the same bytes as the product kernel.
     The variant is read once per process, so each runs in its own interpreter."""
     import os
     import subprocess
@@ -147,7 +148,7 @@ def test_kernel_variants_agree(rt, O):
     root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
     digests = {}
     for variant in ("lanes", "simple", "pools", "deferred", "wave", "wq"):
-        env = dict(os.environ, RT_B200_BVH_KERNEL=variant)
+        env = dict(os.environ, RT_B200_BVH_KERNEL=variant, RT_B200_LIB="exp")
         out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
         assert out.returncode == 0, (variant, out.stderr[-500:])
         digests[variant] = out.stdout.strip().splitlines()[-1]
@@ -156,6 +157,10 @@ def test_kernel_variants_agree(rt, O):
 
     ref, _ = O.render_frame(rt.scenes.synthetic_spheres(300, 5), rt.scenes.ground_plane(), 160, 96, 3, 5, seed=4)
     assert hashlib.sha256(ref.tobytes()).hexdigest() == digests["lanes"]
+    # ... and the product library (no A/B code in it) renders the same bytes
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-500:]
+    assert out.stdout.strip().splitlines()[-1] == digests["lanes"]
 
 
 def test_device_built_tree_agrees(rt, O):

@@ -21,7 +21,7 @@ def test_library_exports_every_declared_symbol(rt):
     assert declared == set(_abi.EXPORTS), declared ^ set(_abi.EXPORTS)
     for name in declared:
         assert hasattr(L, name), name
-    assert L.rt_abi_version() == 1
+    assert L.rt_abi_version() == 2
 
 
 def test_struct_layouts_match_header(rt):
