@@ -175,10 +175,9 @@ int launch(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, const LaunchAr
         if (src) return src;
     }
 #endif
-    const DevScene dev = scene_view(scene);
-    // a second pass keeps the counters of the first (rays add up); only its tickets restart
-    if (a.pixel_list) CK(ctx, cudaMemsetAsync(ctx->d_ctr + RT_CTR_TICKETS, 0, (2 + MAX_SLABS) * sizeof(unsigned long long), ctx->stream));
-    else CK(ctx, cudaMemsetAsync(ctx->d_ctr, 0, RT_CTR_SLOTS * sizeof(unsigned long long), ctx->stream));
+    DevScene dev = scene_view(scene);
+    if (a.force_noaux) dev.aux_ready = 0;
+    CK(ctx, cudaMemsetAsync(ctx->d_ctr, 0, RT_CTR_SLOTS * sizeof(unsigned long long), ctx->stream));
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CK(ctx, launch_render(dev, r.cam, pr, r.isect, r.p.collect_counters != 0, ctx->sm_count, ctx->smem_optin, ctx->stream, info));
     CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -201,35 +200,53 @@ int finish_redo(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, const Lau
     int rc = read_counters(ctx);
     if (rc) return rc;
     const unsigned long long want = ctx->h_ctr[RT_CTR_REDO];
+    ctx->first_pass_ms = 0.0f;
     if (want == 0) return RT_OK;
-    float first_ms = 0.0f;
-    cudaEventElapsedTime(&first_ms, ctx->ev0, ctx->ev1);
+    cudaEventElapsedTime(&ctx->first_pass_ms, ctx->ev0, ctx->ev1);  // the later passes re-record the events
     rc = scene_settle(ctx, scene);  // the tables must be there now
     if (rc) return rc;
     LaunchInfo li;
-    if (want <= RT_REDO_CAP) {
-        LaunchArgs b = a;
-        b.pixel_list = ctx->d_redo;
-        b.list_count = (uint32_t)want;
-        rc = launch(ctx, scene, r, b, &li);
-        *redone = (uint32_t)want;
-    } else {  // more than the list holds: the whole launch again (frame counters untouched: ctl off) ...
+    if (want > RT_REDO_CAP) {
+        // more than the list holds: the whole launch again (frame counters untouched: ctl off); its counters are final
+        unsigned long long slab_counts[MAX_SLABS];
+        memcpy(slab_counts, ctx->h_ctr + RT_CTR_REDO_SLAB, sizeof slab_counts);
         LaunchArgs b = a;
         b.ctl = nullptr;
         rc = launch(ctx, scene, r, b, &li);
+        if (rc) return rc;
         *redone = 0xffffffffu;
-        // ... and the deferred pixels are counted now, slab by slab (the first pass kept their numbers; the relaunch
-        // above zeroed the device copy, the pinned mirror read before it still has them)
-        if (!rc && a.defer_redo && a.ctl) {
-            CK(ctx, cudaMemcpyAsync(ctx->d_ctr + RT_CTR_REDO_SLAB, ctx->h_ctr + RT_CTR_REDO_SLAB, MAX_SLABS * sizeof(unsigned long long),
+        if (a.defer_redo && a.ctl) {  // the deferred pixels are counted now, slab by slab (the first pass kept their numbers)
+            memcpy(ctx->h_ctr + RT_CTR_REDO_SLAB, slab_counts, sizeof slab_counts);
+            CK(ctx, cudaMemcpyAsync(ctx->d_ctr + RT_CTR_REDO_SLAB, ctx->h_ctr + RT_CTR_REDO_SLAB, sizeof slab_counts,
                                     cudaMemcpyHostToDevice, ctx->stream));
             CK(ctx, launch_add_counts(a.ctl->done, ctx->d_ctr + RT_CTR_REDO_SLAB, MAX_SLABS, ctx->stream));
         }
+        return read_counters(ctx);
     }
+    // The listed pixels again.  Counters of the final image = first pass - (the listed pixels as the first pass saw
+    // them: traced once more without the tables, into nothing but the counters) + (the listed pixels with the tables).
+    unsigned long long first[NUM_COUNTERS], minus[NUM_COUNTERS];
+    memcpy(first, ctx->h_ctr, sizeof first);
+    LaunchArgs b = a;
+    b.pixel_list = ctx->d_redo;
+    b.list_count = (uint32_t)want;
+    b.force_noaux = true;
+    b.ctl = nullptr;
+    rc = launch(ctx, scene, r, b, &li);
     if (rc) return rc;
     rc = read_counters(ctx);
     if (rc) return rc;
-    // the counter block now holds both passes: `rays` includes the second pass (stats.redo_pixels says so)
+    memcpy(minus, ctx->h_ctr, sizeof minus);
+    b.force_noaux = false;
+    b.ctl = a.ctl;
+    rc = launch(ctx, scene, r, b, &li);
+    if (rc) return rc;
+    rc = read_counters(ctx);
+    if (rc) return rc;
+    for (int i = 0; i < NUM_COUNTERS; i++) ctx->h_ctr[i] = first[i] - minus[i] + ctx->h_ctr[i];
+    float ms = 0.0f;
+    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
+    *redone = (uint32_t)want;
     return RT_OK;
 }
 
@@ -258,7 +275,7 @@ int finish_stats(rt_ctx* ctx, const Resolved& r, uint64_t pixels, rt_stats* st,
     st->total_lane_iters = c[CTR_TOTAL_LANES];
     float ms = 0.0f;
     CK(ctx, cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1));
-    st->kernel_ms = ms;
+    st->kernel_ms = ms + ctx->first_pass_ms;
     st->total_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t0).count();
     st->intersector_used = (uint32_t)r.isect;
     st->kernel_launches = li.launches + (redo ? 1u : 0u);

@@ -43,6 +43,7 @@ struct rt_ctx {
     unsigned int* d_redo = nullptr;       // pixels to render again once the tie-break tables are up (REDO_CAP entries)
     unsigned int* h_flag = nullptr;       // pinned + mapped: [0] a slab wait timed out
     float* d_scratch = nullptr;
+    float first_pass_ms = 0.0f;           // kernel time of the first pass when a second one followed (finish_redo)
     rtb::DeviceBuild dbuild;
     // scene upload: one pinned staging buffer the blob is assembled in, and a few retired device blobs kept for the
     // next rt_scene_create (a slave makes one scene per job: cudaMalloc/cudaFree per job were a third of a small job)
@@ -128,6 +129,7 @@ struct LaunchArgs {
     // the frame belongs to another rank that may copy a slab out the moment its count is complete: pixels that need a
     // second pass are counted by that pass, not before
     bool defer_redo = false;
+    bool force_noaux = false;  // second-pass accounting: trace as if the tie-break tables had not landed (counters only)
 };
 // The context's own staging frame (+ control block) for a launch of `rows` rows: fills dst / ctl / plan, bumps out_seq.
 int own_frame(rt_ctx* ctx, uint32_t width, uint32_t rows, LaunchArgs* a);

@@ -44,7 +44,7 @@ struct DevScene {
     // visits; the tree then covers the remaining primitives only (ltree == 0: nothing remains, no traversal).
     uint32_t nbig;
     int ltree;
-    uint32_t big_pid[MAX_BIG];
+    const int* big_code;   // [nbig] their leaf codes ~(pid << 5), in HBM: the traversal stack starts with them
     const float4* mat;     // [ns+nt] albedo rgb, roughness
     const float* emis;     // [ns+nt]
     const uint32_t* rank;  // [ns+nt] DFS leaf rank in the REFERENCE tree (exact-distance tie-break, shapes/mod.rs:177-182)
@@ -58,6 +58,7 @@ struct DevScene {
                            // a query that needs them marks its pixel for a second pass instead
     uint32_t ns, nt, ni;   // ni = inner nodes of the reference tree
 #ifdef RT_B200_EXPERIMENTS
+    uint32_t big_pid[MAX_BIG];  // the big primitives' ids, as the A/B kernels read them
     // the reference-topology tree in the first kernels' formats (A/B kernels under csrc/experiments/ only)
     const float4* node_a;  // [ni]    l.min.xyz, l.max.x
     const float4* node_b;  // [ni]    l.max.yz,  r.min.xy
@@ -273,7 +274,7 @@ __device__ __forceinline__ bool sphere_root_exact(V3 d, V3 oc, float r2, float* 
     float disc = x_sub(x_mul(b, b), x_mul(4.0f, c));  // a1*a1 - 4*a2*a0, a2 = 1
     if (disc < 0.0f) return false;
     if (disc == 0.0f) {
-        float x = x_div(-b, 2.0f);
+        float x = x_mul(-b, 0.5f);  // -a1 / (2*a2): a division by two is exact, and so is this product
         if (!in_range(x)) return false;
         *t_out = x;
         return true;
@@ -291,10 +292,10 @@ __device__ __forceinline__ bool sphere_root_exact(V3 d, V3 oc, float r2, float* 
     if (fabsf(same_sign) > 2.0f) {
         float a0x2 = x_mul(2.0f, c);
         x1 = x_div(a0x2, same_sign);
-        x2 = (fabsf(diff_sign) > 2.0f) ? x_div(a0x2, diff_sign) : x_div(same_sign, 2.0f);
+        x2 = (fabsf(diff_sign) > 2.0f) ? x_div(a0x2, diff_sign) : x_mul(same_sign, 0.5f);
     } else {
-        x1 = x_div(diff_sign, 2.0f);
-        x2 = x_div(same_sign, 2.0f);
+        x1 = x_mul(diff_sign, 0.5f);
+        x2 = x_mul(same_sign, 0.5f);
     }
     float lo, hi;
     if (x1 < x2) {

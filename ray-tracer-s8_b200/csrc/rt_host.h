@@ -27,6 +27,9 @@ struct Tunables {
     bool timing = false;         // RT_B200_TIMING: stage times of rt_scene_create on stderr
     int slabs = 16;              // RT_B200_SLABS: slabs a frame download is streamed in
     bool async_ref = true;       // RT_B200_ASYNC_REF=0: build the reference-topology tree inside rt_scene_create
+    int pid_order = 1;           // RT_B200_PID_ORDER=world: primitive ids in world order instead of the traversal tree's DFS order
+    int aux_delay_ms = 0;        // RT_B200_AUX_DELAY_MS: the builder thread sleeps first (tests: frames rendered before the tables land)
+    bool count_done = true;      // RT_B200_COUNT_DONE=0: no completion counters (frames are copied after the kernel)
 #ifdef RT_B200_EXPERIMENTS
     int bvh_variant = 3;         // RT_B200_BVH_KERNEL=lanes|simple|pools|deferred|wave|wq
     int sched_minb = 2;

@@ -61,19 +61,75 @@ __device__ __forceinline__ void mbar_wait(unsigned long long* bar, uint32_t pari
 }
 
 // ---------------------------------------------------------------------------------------------
+// Output stage helpers (cold code, out of line: the hot loop's instruction footprint matters more than a call here)
+// ---------------------------------------------------------------------------------------------
+struct OutDesc {  // where finished pixels go (by value: never a reference to the kernel's parameter block)
+    uint8_t* out;
+    unsigned long long* done;
+    uint32_t width, out_row0, row0, slab_tile_rows;
+};
+__device__ __forceinline__ uint32_t slab_of_row(const OutDesc& od, uint32_t y) { return ((y - od.row0) / TILE_H) / od.slab_tile_rows; }
+
+// All 32 lanes: write the staged pixels `mask` of a tile (st = its 96 staged bytes, origin x0 / y0) to the frame and
+// release their count (minus `hold` pixels that the second pass will count).  whole: the tile is complete.
+__device__ __noinline__ void flush_tile(const OutDesc od, const uint8_t* st, uint32_t x0, uint32_t y0, uint32_t mask, bool whole,
+                                        uint32_t hold) {
+    const int lane = threadIdx.x & 31;
+    const bool vec = whole && mask == 0xffffffffu && ((od.width & 7u) == 0) && ((reinterpret_cast<uintptr_t>(od.out) & 7u) == 0);
+    if (vec) {  // twelve 8-byte vectors: 3 per tile row
+        if (lane < 12) {
+            const uint32_t r = lane / 3, seg = lane % 3;
+            const size_t off = ((size_t)(y0 + r - od.out_row0) * od.width + x0) * 3 + seg * 8;
+            *reinterpret_cast<uint2*>(od.out + off) = *reinterpret_cast<const uint2*>(st + r * 24 + seg * 8);
+        }
+    } else if ((mask >> lane) & 1u) {
+        const size_t off = ((size_t)(y0 + (lane >> 3) - od.out_row0) * od.width + x0 + (lane & 7)) * 3;
+        od.out[off + 0] = st[lane * 3 + 0];
+        od.out[off + 1] = st[lane * 3 + 1];
+        od.out[off + 2] = st[lane * 3 + 2];
+    }
+    if (od.done) {
+        __syncwarp();
+        const uint32_t cnt = (uint32_t)__popc(mask) - hold;
+        if (lane == 0 && cnt) {
+            __threadfence_system();  // cumulative over the warp's stores ordered by the barrier above
+            atomicAdd(&od.done[slab_of_row(od, y0)], (unsigned long long)cnt);
+        }
+    }
+}
+
+// One lane: a finished pixel straight to the frame (no stage slot, or the slot was evicted), counted unless held.
+__device__ __noinline__ void store_pixel(const OutDesc od, uint32_t x, uint32_t y, uint32_t rgb, bool count) {
+    const size_t off = ((size_t)(y - od.out_row0) * od.width + x) * 3;
+    od.out[off + 0] = (uint8_t)rgb;
+    od.out[off + 1] = (uint8_t)(rgb >> 8);
+    od.out[off + 2] = (uint8_t)(rgb >> 16);
+    if (od.done && count) {
+        __threadfence_system();
+        atomicAdd(&od.done[slab_of_row(od, y)], 1ull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // The megakernel
 // ---------------------------------------------------------------------------------------------
+// per-lane state word                       warp-uniform state word
+constexpr uint32_t L_HAVE = 1u;           constexpr uint32_t W_TILES_LEFT = 1u;
+constexpr uint32_t L_FINISHED = 2u;       constexpr uint32_t W_IN_TAIL = 2u;
+constexpr uint32_t L_PEND = 4u;           constexpr int W_SLOT_SHIFT = 4;    // 3 bits: slot + 1 of the warp's current tile
+constexpr uint32_t L_REDO = 8u;           constexpr int W_NEXT_SHIFT = 8;    // 6 bits: next pixel of the current tile
+constexpr int L_SLOT_SHIFT = 4;           // 3 bits: output-stage slot + 1 of this lane's pixel (0: straight to the frame)
+
 template <int ISECT, bool SMEM, bool COUNT, bool STAGE, int MINB, int TPB>
 __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene sc, const DevCamera cam,
                                                                 const DevParams pr) {
     extern __shared__ float4 smem_dyn[];
     constexpr int NW = TPB / 32;
-    // output stage, per warp: OUT_SLOTS tiles of RGB8 + which tile each slot holds, which of its pixels are staged,
-    // which exist (edge tiles are partial), and where it goes
+    // output stage, per warp: OUT_SLOTS tiles of RGB8 + which tile each slot holds (key = tile index in this launch's
+    // grid), which of its pixels are staged, which exist (edge tiles are partial), how many staged pixels are held back
     __shared__ __align__(16) uint8_t s_stage[STAGE ? NW : 1][OUT_SLOTS][TILE_BYTES];
     __shared__ uint32_t s_key[STAGE ? NW : 1][OUT_SLOTS], s_fill[STAGE ? NW : 1][OUT_SLOTS],
-        s_valid[STAGE ? NW : 1][OUT_SLOTS], s_x0[STAGE ? NW : 1][OUT_SLOTS], s_y0[STAGE ? NW : 1][OUT_SLOTS],
-        s_hold[STAGE ? NW : 1][OUT_SLOTS];  // staged pixels of the slot that must not be counted yet (defer_redo)
+        s_valid[STAGE ? NW : 1][OUT_SLOTS], s_hold[STAGE ? NW : 1][OUT_SLOTS];
     __shared__ __align__(8) unsigned long long s_bar;
 
     const unsigned FULL = 0xffffffffu;
@@ -126,76 +182,47 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
     for (int i = 0; i < NUM_COUNTERS; i++) ctr.v[i] = 0;
     unsigned long long rays = 0;
 
-    bool have_px = false, finished = false;
+    uint32_t st = 0;                 // per-lane state word (L_*)
+    uint32_t ws = W_TILES_LEFT | ((uint32_t)TILE_PIX << W_NEXT_SHIFT);  // warp-uniform state word (W_*): no tile yet
+    uint32_t tile_g = 0;             // warp-uniform: tile index (row-major in this launch's grid) of the current tile
     uint32_t px = 0, py = 0, s = 0, left = 0, np = 0;
     float sr = 0.0f, sg = 0.0f, sb = 0.0f;
     Rng rng;
     rng.s0 = rng.s1 = rng.s2 = rng.s3 = 0;
     V3 o = mk(0, 0, 0), d = mk(0, 0, 1);
     uint32_t path[MAX_PATH];  // pids of the non-terminal hits of the current sample
-    int my_slot = -1;         // output-stage slot of this lane's pixel (-1: stores go straight to the frame)
-    bool pend = false;        // this lane staged a finished pixel since the last hand-out
-    bool redo = false;        // a query of this pixel needed the tie-break tables before they had landed
-
-    uint32_t tile_next = TILE_PIX;  // warp-uniform tile cursor (exhausted)
-    uint32_t tile_x0 = 0, tile_y0 = 0;
-    int tile_slot = -1;             // warp-uniform: output-stage slot of the warp's current tile
-    bool tiles_left = true, in_tail = false;
 
     // ticket → tile of this rank: group k of `tile_ranks` tiles, rotated; bottom-up so the sky rows end the launch
-    auto tile_of_ticket = [&](unsigned int k) -> uint64_t {
-        uint64_t g = (uint64_t)k * pr.tile_ranks + (pr.tile_rank + k) % pr.tile_ranks;
+    auto tile_of_ticket = [&](uint32_t k) -> uint32_t {
+        uint32_t g = k * pr.tile_ranks + (pr.tile_rank + k) % pr.tile_ranks;
         if (g < total_tiles && pr.tile_order_reverse) g = total_tiles - 1 - g;
         return g;
     };
-    auto slab_of_row = [&](uint32_t y) -> uint32_t { return ((y - pr.row0) / TILE_H) / pr.slab_tile_rows; };
-    // all 32 lanes: write the staged pixels `mask` of slot sl to the frame and count them
-    auto flush_slot = [&](int sl, uint32_t mask, bool whole) {
-        const uint32_t x0 = s_x0[warp][sl], y0 = s_y0[warp][sl];
-        const uint8_t* st = s_stage[warp][sl];
-        const bool vec = whole && mask == FULL && ((pr.width & 7u) == 0) && ((reinterpret_cast<uintptr_t>(pr.out) & 7u) == 0);
-        if (vec) {  // twelve 8-byte vectors: 3 per tile row
-            if (lane < 12) {
-                const uint32_t r = lane / 3, seg = lane % 3;
-                const size_t off = ((size_t)(y0 + r - pr.out_row0) * pr.width + x0) * 3 + seg * 8;
-                *reinterpret_cast<uint2*>(pr.out + off) = *reinterpret_cast<const uint2*>(st + r * 24 + seg * 8);
-            }
-        } else if ((mask >> lane) & 1u) {
-            const size_t off = ((size_t)(y0 + (lane >> 3) - pr.out_row0) * pr.width + x0 + (lane & 7)) * 3;
-            pr.out[off + 0] = st[lane * 3 + 0];
-            pr.out[off + 1] = st[lane * 3 + 1];
-            pr.out[off + 2] = st[lane * 3 + 2];
-        }
-        if (pr.done) {
-            __syncwarp();
-            if (lane == 0) {
-                const uint32_t cnt = (uint32_t)__popc(mask) - s_hold[warp][sl];
-                s_hold[warp][sl] = 0u;
-                __threadfence_system();  // cumulative over the warp's stores ordered by the barrier above
-                if (cnt) atomicAdd(&pr.done[slab_of_row(y0)], (unsigned long long)cnt);
-            }
-        }
-    };
+    auto out_desc = [&]() { return OutDesc{pr.out, pr.done, pr.width, pr.out_row0, pr.row0, pr.slab_tile_rows}; };
 
     for (;;) {
         // ---- hand out pixels: warp-cooperative, tile by tile ----
-        unsigned want = __ballot_sync(FULL, !have_px && !finished);
-        if (STAGE && want) {
-            // collect the pixels staged since the last hand-out; a tile whose pixels are all staged leaves as vectors
-            if (__ballot_sync(FULL, pend)) {
+        unsigned want = __ballot_sync(FULL, (st & (L_HAVE | L_FINISHED)) == 0);
+        if (want) {
+            if (STAGE && __ballot_sync(FULL, st & L_PEND)) {
+                // collect the pixels staged since the last hand-out; a tile whose pixels are all staged leaves as vectors
                 const uint32_t bit = 1u << ((px & (TILE_W - 1)) + TILE_W * ((py - pr.row0) & (TILE_H - 1)));
-#pragma unroll
+                const int my_sl = (int)((st >> L_SLOT_SHIFT) & 7u) - 1;
+#pragma unroll 1
                 for (int sl = 0; sl < OUT_SLOTS; sl++) {
-                    const uint32_t add = __reduce_or_sync(FULL, (pend && my_slot == sl) ? bit : 0u);
+                    const uint32_t add = __reduce_or_sync(FULL, ((st & L_PEND) && my_sl == sl) ? bit : 0u);
                     if (add) {
                         const uint32_t nf = s_fill[warp][sl] | add;
                         __syncwarp();
                         if (nf == s_valid[warp][sl]) {
-                            flush_slot(sl, nf, true);
+                            const uint32_t g = s_key[warp][sl];
+                            flush_tile(out_desc(), s_stage[warp][sl], (g % pr.tiles_x) * TILE_W, pr.row0 + (g / pr.tiles_x) * TILE_H,
+                                       nf, true, s_hold[warp][sl]);
                             __syncwarp();
                             if (lane == 0) {
                                 s_key[warp][sl] = KEY_FREE;
                                 s_fill[warp][sl] = 0u;
+                                s_hold[warp][sl] = 0u;
                             }
                         } else if (lane == 0) {
                             s_fill[warp][sl] = nf;
@@ -203,120 +230,106 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                         __syncwarp();
                     }
                 }
-                pend = false;
+                st &= ~L_PEND;
             }
-        }
-        while (want) {
-            if (tile_next >= (uint32_t)TILE_PIX) {
-                if (!tiles_left) {
-                    if (!have_px) finished = true;
-                    break;
-                }
-                if (!in_tail) {
-                    unsigned int k = 0;
+            while (want) {
+                // (1) warp-uniform: a unit to hand out from — the current tile, a new tile, or the tail's pixel tickets
+                if (((ws >> W_NEXT_SHIFT) & 63u) >= (uint32_t)TILE_PIX && !(ws & W_IN_TAIL)) {
+                    if (!(ws & W_TILES_LEFT)) {
+                        if (!(st & L_HAVE)) st |= L_FINISHED;
+                        break;
+                    }
+                    uint32_t k = 0;
                     if (lane == 0) k = atomicAdd(&pr.tile_counter[0], 1u);
                     k = __shfl_sync(FULL, k, 0);
-                    if (k >= pr.tail_first) {
-                        in_tail = true;
+                    const uint32_t g = k < pr.tail_first ? tile_of_ticket(k) : total_tiles;
+                    if (g >= total_tiles) {  // the whole-tile tickets are gone (only the last ticket group can be short)
+                        ws |= W_IN_TAIL;
                     } else {
-                        const uint64_t g = tile_of_ticket(k);
-                        if (g >= total_tiles) {  // only the last ticket group can be short
-                            in_tail = true;
-                        } else {
-                            tile_x0 = (uint32_t)(g % pr.tiles_x) * TILE_W;
-                            tile_y0 = pr.row0 + (uint32_t)(g / pr.tiles_x) * TILE_H;
-                            tile_next = 0;
-                            if (STAGE) {
-                                // a free slot, else evict one: its staged pixels leave as bytes and the lanes still
-                                // working on that tile will find the key changed and store directly
-                                int sl = -1;
+                        tile_g = g;
+                        ws &= ~((63u << W_NEXT_SHIFT) | (7u << W_SLOT_SHIFT));  // next = 0, no slot
+                        if (STAGE) {
+                            // a free slot, else evict one: its staged pixels leave as bytes and the lanes still
+                            // working on that tile will find the key changed and store directly
+                            int sl = -1;
 #pragma unroll
-                                for (int i = OUT_SLOTS - 1; i >= 0; i--)
-                                    if (s_key[warp][i] == KEY_FREE) sl = i;
-                                if (sl < 0) {
-                                    sl = (int)(k % OUT_SLOTS);
-                                    const uint32_t f = s_fill[warp][sl];
-                                    __syncwarp();
-                                    if (f) flush_slot(sl, f, false);
-                                }
-                                const bool v = (tile_x0 + (lane & 7) < pr.width) && (tile_y0 + (lane >> 3) < pr.row1);
-                                const uint32_t vm = __ballot_sync(FULL, v);
-                                if (lane == 0) {
-                                    s_key[warp][sl] = (uint32_t)g;
-                                    s_fill[warp][sl] = 0u;
-                                    s_hold[warp][sl] = 0u;
-                                    s_valid[warp][sl] = vm;
-                                    s_x0[warp][sl] = tile_x0;
-                                    s_y0[warp][sl] = tile_y0;
-                                }
+                            for (int i = OUT_SLOTS - 1; i >= 0; i--)
+                                if (s_key[warp][i] == KEY_FREE) sl = i;
+                            if (sl < 0) {
+                                sl = (int)(k % OUT_SLOTS);
+                                const uint32_t f = s_fill[warp][sl], og = s_key[warp][sl];
                                 __syncwarp();
-                                tile_slot = sl;
+                                if (f) flush_tile(out_desc(), s_stage[warp][sl], (og % pr.tiles_x) * TILE_W,
+                                                  pr.row0 + (og / pr.tiles_x) * TILE_H, f, false, s_hold[warp][sl]);
                             }
+                            const uint32_t x0 = (g % pr.tiles_x) * TILE_W, y0 = pr.row0 + (g / pr.tiles_x) * TILE_H;
+                            const uint32_t vm = __ballot_sync(FULL, (x0 + (lane & 7) < pr.width) && (y0 + (lane >> 3) < pr.row1));
+                            __syncwarp();
+                            if (lane == 0) {
+                                s_key[warp][sl] = g;
+                                s_fill[warp][sl] = 0u;
+                                s_hold[warp][sl] = 0u;
+                                s_valid[warp][sl] = vm;
+                            }
+                            __syncwarp();
+                            ws |= (uint32_t)(sl + 1) << W_SLOT_SHIFT;
                         }
                     }
                 }
-                if (in_tail) {
-                    // the tail of the launch: pixel tickets, one per wanting lane
-                    unsigned int base = 0;
+                // (2) per wanting lane: a candidate pixel (x == width: none)
+                uint32_t x = pr.width, y = 0, slot1 = 0;
+                const uint32_t my = __popc(want & lt_mask);
+                const bool wants = (st & (L_HAVE | L_FINISHED)) == 0;
+                if (ws & W_IN_TAIL) {
+                    // the tail of the launch (or a second pass over a pixel list): pixel tickets, one per wanting lane
+                    uint32_t base = 0;
                     if (lane == 0) base = atomicAdd(&pr.tile_counter[1], (unsigned int)__popc(want));
                     base = __shfl_sync(FULL, base, 0);
                     if (base >= tail_pixels) {
-                        tiles_left = false;
-                        if (!have_px) finished = true;
+                        ws &= ~(W_TILES_LEFT | W_IN_TAIL);
+                        if (!(st & L_HAVE)) st |= L_FINISHED;
                         break;
                     }
-                    const uint32_t idx = base + __popc(want & lt_mask);
-                    if (!have_px && !finished && idx < tail_pixels) {
-                        uint32_t x = pr.width, y = 0;
+                    const uint32_t idx = base + my;
+                    if (wants && idx < tail_pixels) {
                         if (pr.pixel_list) {  // second pass: exactly the listed pixels
                             const uint32_t p = pr.pixel_list[idx];
                             x = p % pr.width;
                             y = p / pr.width;
                         } else {
-                            const uint64_t g = tile_of_ticket(pr.tail_first + idx / TILE_PIX);
+                            const uint32_t g = tile_of_ticket(pr.tail_first + idx / TILE_PIX);
                             const uint32_t j = idx % TILE_PIX;
                             if (g < total_tiles) {
-                                x = (uint32_t)(g % pr.tiles_x) * TILE_W + (j & (TILE_W - 1));
-                                y = pr.row0 + (uint32_t)(g / pr.tiles_x) * TILE_H + (j / TILE_W);
+                                x = (g % pr.tiles_x) * TILE_W + (j & (TILE_W - 1));
+                                y = pr.row0 + (g / pr.tiles_x) * TILE_H + (j / TILE_W);
                             }
                         }
-                        if (x < pr.width && y < pr.row1) {
-                            px = x; py = y;
-                            have_px = true;
-                            my_slot = -1;
-                            redo = false;
-                            rng.seed_from_u64(pr.seed + ((uint64_t)y * pr.width + x));
-                            sr = sg = sb = 0.0f;
-                            s = 0;
-                            left = 0;
-                        }
                     }
-                    want = __ballot_sync(FULL, !have_px && !finished);
-                    continue;
+                } else {
+                    const uint32_t next = (ws >> W_NEXT_SHIFT) & 63u, avail = (uint32_t)TILE_PIX - next;
+                    if (wants && my < avail) {
+                        const uint32_t j = next + my;
+                        x = (tile_g % pr.tiles_x) * TILE_W + (j & (TILE_W - 1));
+                        y = pr.row0 + (tile_g / pr.tiles_x) * TILE_H + (j / TILE_W);
+                        slot1 = (ws >> W_SLOT_SHIFT) & 7u;
+                    }
+                    ws += min((uint32_t)__popc(want), avail) << W_NEXT_SHIFT;
                 }
-            }
-            const uint32_t avail = TILE_PIX - tile_next;
-            const uint32_t my = __popc(want & lt_mask);
-            if (!have_px && !finished && my < avail) {
-                const uint32_t j = tile_next + my;
-                const uint32_t x = tile_x0 + (j & (TILE_W - 1)), y = tile_y0 + (j / TILE_W);
-                if (x < pr.width && y < pr.row1) {  // tiles on the right/bottom edge are partial
+                // (3) the lane takes its pixel (tiles on the right / bottom edge are partial)
+                if (x < pr.width && y < pr.row1) {
                     px = x; py = y;
-                    have_px = true;
-                    my_slot = tile_slot;
-                    redo = false;
+                    st = L_HAVE | (slot1 << L_SLOT_SHIFT);
                     rng.seed_from_u64(pr.seed + ((uint64_t)y * pr.width + x));
                     sr = sg = sb = 0.0f;
                     s = 0;
                     left = 0;
                 }
+                want = __ballot_sync(FULL, (st & (L_HAVE | L_FINISHED)) == 0);
             }
-            tile_next += min((uint32_t)__popc(want), avail);
-            want = __ballot_sync(FULL, !have_px && !finished);
         }
-        if (__ballot_sync(FULL, have_px) == 0) break;
+        if (__ballot_sync(FULL, st & L_HAVE) == 0) break;
 
-        if (have_px) {
+        if (st & L_HAVE) {
             if (left == 0) {  // start sample s
                 primary_ray(cam, px, pr.height - py - 1, rng, &o, &d);  // y_cam = h - y - 1 (main.rs:71)
                 left = pr.depth;
@@ -344,7 +357,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
             Hit h;
             if (ISECT == RT_INTERSECT_BRUTE) trace_brute<COUNT>(sc, sv, o, d, h, ctr);
             else trace_bvh_ch<COUNT>(sc, sv, o, d, h, ctr);
-            redo = redo || h.unsure;
+            if (h.unsure) st |= L_REDO;
 
             bool done;
             float Lr, Lg, Lb;
@@ -390,6 +403,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
             }
             if (done) {
                 // fold albedo ⊙ (albedo ⊙ (... ⊙ L)) innermost first, like the recursion unwinding
+#pragma unroll 1
                 while (np > 0) {
                     const float4 m = __ldg(&sc.mat[path[--np]]);
                     Lr = x_mul(m.x, Lr); Lg = x_mul(m.y, Lg); Lb = x_mul(m.z, Lb);
@@ -398,35 +412,27 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                 s++;
                 left = 0;
                 if (s == pr.spp) {  // pixel finished (main.rs:78-81)
-                    const uint32_t qr = quantise(sr, spp_f), qg = quantise(sg, spp_f), qb = quantise(sb, spp_f);
-                    const bool hold = redo && pr.defer_redo;  // final only after the second pass: not counted now
+                    const uint32_t rgb = quantise(sr, spp_f) | (quantise(sg, spp_f) << 8) | (quantise(sb, spp_f) << 16);
+                    // a pixel that goes to the second pass of a rank that does not own the frame is counted there
+                    const bool hold = (st & L_REDO) && pr.defer_redo;
+                    const int my_sl = (int)((st >> L_SLOT_SHIFT) & 7u) - 1;
                     bool staged = false;
-                    if (STAGE && my_slot >= 0) {
+                    if (STAGE && my_sl >= 0) {
                         const uint32_t key = ((py - pr.row0) / TILE_H) * pr.tiles_x + px / TILE_W;
-                        if (s_key[warp][my_slot] == key) {  // the slot still holds this pixel's tile (not evicted)
-                            uint8_t* st = s_stage[warp][my_slot] + 3 * ((px & (TILE_W - 1)) + TILE_W * ((py - pr.row0) & (TILE_H - 1)));
-                            st[0] = (uint8_t)qr; st[1] = (uint8_t)qg; st[2] = (uint8_t)qb;
-                            if (hold) atomicAdd(&s_hold[warp][my_slot], 1u);
-                            pend = true;
+                        if (s_key[warp][my_sl] == key) {  // the slot still holds this pixel's tile (not evicted)
+                            uint8_t* dst = s_stage[warp][my_sl] + 3 * ((px & (TILE_W - 1)) + TILE_W * ((py - pr.row0) & (TILE_H - 1)));
+                            dst[0] = (uint8_t)rgb; dst[1] = (uint8_t)(rgb >> 8); dst[2] = (uint8_t)(rgb >> 16);
+                            if (hold) atomicAdd(&s_hold[warp][my_sl], 1u);
                             staged = true;
                         }
                     }
-                    if (!staged) {
-                        const size_t off = ((size_t)(py - pr.out_row0) * pr.width + px) * 3;
-                        pr.out[off + 0] = (uint8_t)qr;
-                        pr.out[off + 1] = (uint8_t)qg;
-                        pr.out[off + 2] = (uint8_t)qb;
-                        if (pr.done && !hold) {
-                            __threadfence_system();
-                            atomicAdd(&pr.done[slab_of_row(py)], 1ull);
-                        }
-                    }
-                    if (redo) {
+                    if (!staged) store_pixel(out_desc(), px, py, rgb, !hold);
+                    if ((st & L_REDO) && !pr.pixel_list) {
                         const unsigned long long at = atomicAdd(pr.redo_count, 1ull);
                         if (at < pr.redo_cap) pr.redo_list[at] = py * pr.width + px;
-                        if (pr.defer_redo) atomicAdd(&pr.redo_slab[slab_of_row(py)], 1ull);
+                        if (pr.defer_redo) atomicAdd(&pr.redo_slab[((py - pr.row0) / TILE_H) / pr.slab_tile_rows], 1ull);
                     }
-                    have_px = false;
+                    st = (st & ~(L_HAVE | L_REDO | L_PEND)) | (staged ? L_PEND : 0u);  // the slot bits stay for the collect
                 }
             }
         }
@@ -529,6 +535,9 @@ const Tunables& tunables() {
         v.timing = std::getenv("RT_B200_TIMING") != nullptr;
         v.slabs = std::max(1, std::min(MAX_SLABS, env_int("RT_B200_SLABS", 16)));
         v.async_ref = env_int("RT_B200_ASYNC_REF", 1) != 0;
+        v.count_done = env_int("RT_B200_COUNT_DONE", 1) != 0;
+        v.pid_order = env_is("RT_B200_PID_ORDER", "world") ? 0 : 1;
+        v.aux_delay_ms = std::max(0, env_int("RT_B200_AUX_DELAY_MS", 0));
 #ifdef RT_B200_EXPERIMENTS
         read_experiment_tunables(&v);
 #endif
@@ -630,6 +639,10 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
     if (grid > want_ctas) grid = want_ctas;
     if (grid < 1) grid = 1;
     DevParams prm = pr;
+    if (!tn.count_done) {
+        prm.done = nullptr;
+        if (info) info->counts_done = false;
+    }
     prm.tile_order_reverse = tn.tile_order_reverse;
     prm.my_tickets = (uint32_t)my_tiles;
     if (pr.pixel_list) {  // second pass over a pixel list: pixel tickets only

@@ -221,13 +221,6 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         if (wrc) return set_err(ctx, wrc, "%s", werr.c_str());
     }
     const std::vector<Box>& boxes = aux->boxes;  // shared, read-only from here on
-    // pids: spheres [0, ns) then triangles [ns, n), each in world order
-    aux->pid_of_world.resize(n);
-    {
-        uint32_t next_s = 0, next_t = n_spheres;
-        for (uint32_t w = 0; w < n; w++) aux->pid_of_world[w] = world[w].kind == 0 ? next_s++ : next_t++;
-    }
-    const std::vector<uint32_t>& pid_of_world = aux->pid_of_world;
     lap("world order + boxes");
 
     // ---- which tree will be traversed ---------------------------------------------------------------------
@@ -285,20 +278,11 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     const bool ref_sync = !tn.async_ref || tree_mode == 0 || legacy || n < 256;
     HostBVH ref_bvh;  // synchronous case only
     AuxTables ref_tables;
-    uint8_t* late_dst = nullptr;  // set once the blob exists (the thread starts after the layout is known)
-    auto build_ref = [&](HostBVH* bvh, AuxTables* tables) -> bool {
-        std::string berr;
-        if (!build_bvh(boxes, bvh, &berr)) {
-            aux->err = berr;
-            return false;
-        }
-        tables_from_tree(*bvh, pid_of_world, tables, &aux->rank_by_world);
-        aux->n_nodes = bvh->node_count;
-        aux->depth = bvh->depth;
-        return true;
-    };
     if (ref_sync) {
-        if (!build_ref(&ref_bvh, &ref_tables)) return set_err(ctx, RT_ERR_BVH, "BVH build failed: %s", aux->err.c_str());
+        std::string berr;
+        if (!build_bvh(boxes, &ref_bvh, &berr)) return set_err(ctx, RT_ERR_BVH, "BVH build failed: %s", berr.c_str());
+        aux->n_nodes = ref_bvh.node_count;
+        aux->depth = ref_bvh.depth;
         lap("reference tree (sync)");
     }
 
@@ -322,10 +306,39 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             return set_err(ctx, RT_ERR_UNSUPPORTED, "traversal tree depth %u exceeds the traversal stack (%d)", T->depth, MAX_STACK);
         sc->tree_depth = T->depth;
     }
+    lap("traversal tree");
+
+    // ---- primitive ids: spheres [0, ns), triangles [ns, n).  In the DFS leaf order of the host-built traversal tree
+    // when there is one (neighbours in space are neighbours in memory: the per-hit material / box / rank reads of the
+    // lanes of a warp share cache lines), else in world order.
+    aux->pid_of_world.assign(n, 0xffffffffu);
+    {
+        uint32_t next_s = 0, next_t = n_spheres;
+        auto give = [&](uint32_t w) {
+            if (aux->pid_of_world[w] == 0xffffffffu) aux->pid_of_world[w] = world[w].kind == 0 ? next_s++ : next_t++;
+        };
+        if (T && tn.pid_order == 1) {
+            std::vector<int32_t> todo;
+            todo.push_back(T->root);
+            while (!todo.empty()) {
+                const int32_t c = todo.back();
+                todo.pop_back();
+                if (c < 0) {
+                    give((uint32_t)~c);
+                } else {
+                    todo.push_back(T->inner[(size_t)c].right);
+                    todo.push_back(T->inner[(size_t)c].left);
+                }
+            }
+        }
+        for (uint32_t w = 0; w < n; w++) give(w);
+    }
+    const std::vector<uint32_t>& pid_of_world = aux->pid_of_world;
+    if (ref_sync) tables_from_tree(ref_bvh, pid_of_world, &ref_tables, &aux->rank_by_world);
     uint32_t lni = 0;
     if (device_tree) lni = (uint32_t)rest.size() - 1;
     else if (T) lni = (uint32_t)T->inner.size();
-    lap("traversal tree");
+    lap("primitive ids");
 
     // ---- blob layout: the shared-memory image first (contiguous, 16-byte granules), then 256-byte aligned sections
     const uint32_t ni_ref = n - 1;
@@ -340,7 +353,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
                  o_ld = o_la + (size_t)lni * 48;
     off = align_up(o_ld + align_up((size_t)lni * 8, 16), 256);
     const size_t o_sph2 = take((size_t)ns8 * 16), o_mat = take((size_t)n * 16), o_em = take((size_t)n * 4),
-                 o_box = take((size_t)n * 32);
+                 o_box = take((size_t)n * 32), o_big = take((size_t)MAX_BIG * 4);
 #ifdef RT_B200_EXPERIMENTS
     const size_t nl = legacy ? (size_t)ni_ref : 0;
     const size_t o_na = take(nl * 16), o_nb = take(nl * 16), o_nc = take(nl * 16), o_nd = take(nl * 8);
@@ -392,13 +405,14 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
 
     // ---- the builder thread starts now: it knows where its tables go ------------------------------------------
     if (!ref_sync) {
-        late_dst = sc->d_blob;
         rt_aux* const a = aux;
         rt_ctx* const c = ctx;
         const size_t dr = o_rank, du = o_up, db = o_refbox;
-        uint8_t* const dst = late_dst;
-        a->worker = std::thread([a, c, dst, dr, du, db] {
+        uint8_t* const dst = sc->d_blob;
+        const int delay_ms = tn.aux_delay_ms;
+        a->worker = std::thread([a, c, dst, dr, du, db, delay_ms] {
             try {
+                if (delay_ms > 0) std::this_thread::sleep_for(std::chrono::milliseconds(delay_ms));
                 HostBVH bvh;
                 AuxTables t;
                 std::string berr;
@@ -497,6 +511,8 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
                 h2[8 * (size_t)j + 6 + k] = real ? g[3] : -std::numeric_limits<float>::infinity();
             }
     }
+    for (size_t i = 0; i < (size_t)MAX_BIG; i++)
+        ((int32_t*)(h + o_big))[i] = i < big_world.size() ? ~(int32_t)(pid_of_world[big_world[i]] << 5) : 0;
     lap("primitive arrays");
 
     // traversal-tree records from the host tree: DFS pre-order numbering, left subtree first
@@ -615,7 +631,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     d.lroot = lroot;
     d.ltree = ltree ? 1 : 0;
     d.nbig = (uint32_t)big_world.size();
-    for (size_t i = 0; i < (size_t)MAX_BIG; i++) d.big_pid[i] = i < big_world.size() ? pid_of_world[big_world[i]] : 0u;
+    d.big_code = (const int*)(sc->d_blob + o_big);
     d.mat = (const float4*)(sc->d_blob + o_mat);
     d.emis = (const float*)(sc->d_blob + o_em);
     d.rank = (const uint32_t*)(sc->d_blob + o_rank);
@@ -627,6 +643,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     d.nt = n_triangles;
     d.ni = ni_ref;
 #ifdef RT_B200_EXPERIMENTS
+    for (size_t i = 0; i < (size_t)MAX_BIG; i++) d.big_pid[i] = i < big_world.size() ? pid_of_world[big_world[i]] : 0u;
     d.node_a = (const float4*)(sc->d_blob + o_na);
     d.node_b = (const float4*)(sc->d_blob + o_nb);
     d.node_c = (const float4*)(sc->d_blob + o_nc);

@@ -19,10 +19,18 @@ constexpr int WARPS = THREADS / 32;
 
 struct Hit {
     float dist;  // length(point - origin), exact domain
-    int pid;     // -1 = miss
+    int pid;     // -1 = miss.  While a query runs, HIT_UNSURE may be set in a non-negative pid (see consider)
     V3 p;        // ray.at(t)
-    bool unsure; // the decision needed the tie-break tables before they had landed: the pixel is rendered again
+    bool unsure; // set by the trace functions when they return: the decision needed the tie-break tables before they
+                 // had landed, the pixel is rendered again
 };
+// Carried in bit 30 of Hit::pid during a query instead of in a register of its own (pids are 26 bits; the kernel
+// runs at its register cap and one more live value in the traversal loop costs more than these few masks).
+constexpr int HIT_UNSURE = 0x40000000;
+__device__ __forceinline__ void hit_finish(Hit& h) {
+    h.unsure = h.pid >= 0 && (h.pid & HIT_UNSURE);
+    if (h.pid >= 0) h.pid &= ~HIT_UNSURE;
+}
 
 struct Ctr {
     unsigned long long v[NUM_COUNTERS];
@@ -66,33 +74,53 @@ __device__ __forceinline__ bool robustly_inside(V3 p, float t, V3 lo, V3 hi, flo
     return ok;
 }
 
+// What consider() reads of the scene, by value: a reference to the kernel's DevScene parameter must never reach an
+// out-of-line function — taking its address makes the compiler copy the whole parameter block to local memory and
+// read `sc.*` from there in the hot loops as well (measured: C3 38 → 50 ms).
+struct HitCtx {
+    const float4* leaf_box;
+    const uint32_t* rank;
+    const uint32_t* ref_up;
+    const float4* ref_box;
+    uint32_t n;
+    int aux_ready;
+};
+__device__ __forceinline__ HitCtx hit_ctx(const DevScene& sc) {
+#ifdef RT_AB_NO_UNSURE  // A/B build: tables assumed present (no second-pass bookkeeping in the kernel)
+    return HitCtx{sc.leaf_box, sc.rank, sc.ref_up, sc.ref_box, sc.ns + sc.nt, 1};
+#else
+    return HitCtx{sc.leaf_box, sc.rank, sc.ref_up, sc.ref_box, sc.ns + sc.nt, sc.aux_ready};
+#endif
+}
+
 // Rays with a direction component of exactly +-0 make the reference's slab test produce inf / NaN planes
 // (ray.rs:133-143,174-194 with the crate's own min/max, ray.rs:82-112), and then "the shape's own box passes"
 // no longer implies that every ancestor's child box passes (e.g. d.z == 0 with o.z exactly on an ancestor's max
 // plane gives tmax = NaN and the subtree is dropped; d.x == -0.0 makes every box fail).  Such rays re-run the
 // reference's own test on every box of the leaf's ancestor chain in the REFERENCE tree, root side last.
-__device__ __noinline__ bool ref_ancestors_pass(const DevScene& sc, V3 o, V3 d, int pid) {
-    const uint32_t n = sc.ns + sc.nt;
-    uint32_t u = __ldg(&sc.ref_up[pid]);  // (parent << 1) | side of the leaf; its own box is tested by the caller
+__device__ __noinline__ bool ref_ancestors_pass(const uint32_t* __restrict__ ref_up, const float4* __restrict__ ref_box,
+                                                uint32_t n, V3 o, V3 d, int pid) {
+    uint32_t u = __ldg(&ref_up[pid]);  // (parent << 1) | side of the leaf; its own box is tested by the caller
     while (u != UP_ROOT) {
-        u = __ldg(&sc.ref_up[n + (u >> 1)]);  // the parent's own slot in ITS parent
-        if (u == UP_ROOT) break;              // the root node's box is never tested (bvh_impl.rs:373-398)
-        const V3 lo = ld3(__ldg(&sc.ref_box[2 * u])), hi = ld3(__ldg(&sc.ref_box[2 * u + 1]));
+        u = __ldg(&ref_up[n + (u >> 1)]);  // the parent's own slot in ITS parent
+        if (u == UP_ROOT) break;           // the root node's box is never tested (bvh_impl.rs:373-398)
+        const V3 lo = ld3(__ldg(&ref_box[2 * u])), hi = ld3(__ldg(&ref_box[2 * u + 1]));
         if (!ref_intersects_aabb(o, d, lo, hi)) return false;
     }
     return true;
 }
 
-__device__ __forceinline__ void consider(const DevScene& sc, V3 o, V3 d, float t, int pid, Hit& best) {
+__device__ __forceinline__ void consider(const HitCtx& hc, V3 o, V3 d, float t, int pid, Hit& best) {
     V3 p = x_add(o, x_scale(d, t));   // Ray::at: origin + t*direction
+    int flag = 0;
     // bvh.traverse() (main.rs:113): the shape is a candidate only if the reference's slab test lets it through
-    if (sc.ns + sc.nt > 1) {
-        const V3 blo = ld3(__ldg(&sc.leaf_box[2 * pid])), bhi = ld3(__ldg(&sc.leaf_box[2 * pid + 1]));
+    if (hc.n > 1) {
+        const V3 blo = ld3(__ldg(&hc.leaf_box[2 * pid])), bhi = ld3(__ldg(&hc.leaf_box[2 * pid + 1]));
         const bool degenerate = (d.x == 0.0f) || (d.y == 0.0f) || (d.z == 0.0f);  // +-0: inf / NaN slabs
         if (degenerate) {
             if (!ref_intersects_aabb(o, d, blo, bhi)) return;
-            if (!sc.aux_ready) best.unsure = true;
-            else if (!ref_ancestors_pass(sc, o, d, pid)) return;
+            if (!hc.aux_ready) flag = HIT_UNSURE;  // whether the ancestors pass is decided in the second pass
+            else if (!ref_ancestors_pass(hc.ref_up, hc.ref_box, hc.n, o, d, pid)) return;
         } else if (!robustly_inside(p, t, blo, bhi) && !ref_intersects_aabb(o, d, blo, bhi)) {
             return;
         }
@@ -103,21 +131,27 @@ __device__ __forceinline__ void consider(const DevScene& sc, V3 o, V3 d, float t
         take = true;
     } else if (best.dist > dist) {
         take = true;
+        flag |= best.pid & HIT_UNSURE;  // sticky for the rest of the query
     } else if (best.dist == dist) {
-        if (sc.aux_ready) {
-            take = __ldg(&sc.rank[pid]) < __ldg(&sc.rank[best.pid]);
+        if (hc.aux_ready) {
+            take = __ldg(&hc.rank[pid]) < __ldg(&hc.rank[best.pid]);
         } else {
             take = false;
-            best.unsure = true;
+            flag = HIT_UNSURE;
         }
     } else {
         take = false;  // includes NaN: partial_cmp → None → Less → incumbent kept
     }
     if (take) {
         best.dist = dist;
-        best.pid = pid;
+        best.pid = pid | flag;
         best.p = p;
+    } else if (flag) {
+        best.pid |= flag;  // best.pid >= 0 here: a candidate is only ever refused in favour of an incumbent
     }
+}
+__device__ __forceinline__ void consider(const DevScene& sc, V3 o, V3 d, float t, int pid, Hit& best) {
+    consider(hit_ctx(sc), o, d, t, pid, best);
 }
 
 template <bool COUNT>
@@ -237,7 +271,7 @@ __device__ __forceinline__ void triangle_exact(const DevScene& sc, const float4*
 // m >= 0  <=>  the reference's discriminant 4*(bh^2 - (|oc|^2 - r^2)) is above -8e-5*|oc|^2 (~300 ulp of slack).
 // Everything else (roots behind the origin, exact roots, slab check, min_by) runs only for the few spheres that pass.
 template <bool COUNT>
-__device__ __noinline__ void brute_sphere_slow(const DevScene& sc, const float4 s, int pid, V3 o, V3 d, Hit& best,
+__device__ __noinline__ void brute_sphere_slow(const HitCtx sc, const float4 s, int pid, V3 o, V3 d, Hit& best,
                                                Ctr& ctr) {
     const V3 oc = mk(x_sub(o.x, s.x), x_sub(o.y, s.y), x_sub(o.z, s.z));
     const float bh = fmaf(oc.z, d.z, fmaf(oc.y, d.y, oc.x * d.x));
@@ -260,7 +294,7 @@ __device__ __forceinline__ float brute_margin(const float4 s, V3 o, V3 d) {
 // a group of 8 spheres (first is a multiple of 8) in which at least one passed the filter: the four pairs once more
 // in packed arithmetic, this time keeping WHICH spheres passed, then the slow path for exactly those
 template <bool COUNT>
-__device__ __noinline__ void brute_group_slow(const DevScene& sc, const float4* sph, const float4* sph2, int first, int count,
+__device__ __noinline__ void brute_group_slow(const HitCtx sc, const float4* sph, const float4* sph2, int first, int count,
                                               V3 o, V3 d, bool all, Hit& best, Ctr& ctr) {
     const f32x2 ox2 = pk2(o.x, o.x), oy2 = pk2(o.y, o.y), oz2 = pk2(o.z, o.z);
     const f32x2 dx2 = pk2(d.x, d.x), dy2 = pk2(d.y, d.y), dz2 = pk2(d.z, d.z);
@@ -287,10 +321,9 @@ __device__ __noinline__ void brute_group_slow(const DevScene& sc, const float4* 
 }
 
 template <bool COUNT>
-__device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
+__device__ __forceinline__ void trace_brute_impl(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
     best.pid = -1;
     best.dist = 0.0f;
-    best.unsure = false;
     const int ns = (int)sc.ns;
     // a non-finite ray makes the margins NaN, which fmaxf would drop: send such a ray through the slow path whole
     const bool weird = !(isfinite(o.x) && isfinite(o.y) && isfinite(o.z) && isfinite(d.x) && isfinite(d.y) && isfinite(d.z));
@@ -312,6 +345,7 @@ __device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView&
     };
     const int ns8 = (ns + 7) & ~7;
     const float NEG = -3.0e38f;
+    const HitCtx hc = hit_ctx(sc);
     int i = 0;
     for (; i + 16 <= ns8; i += 16) {
         float m0 = NEG, m1 = NEG;
@@ -322,8 +356,8 @@ __device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView&
         }
         if (COUNT) ctr.v[CTR_SPH_TEST] += min(16, ns - i);
         if (!(fmaxf(m0, m1) < 0.0f) || weird) {
-            if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, sv.sph2, i, min(8, ns - i), o, d, weird, best, ctr);
-            if ((!(m1 < 0.0f) || weird) && i + 8 < ns) brute_group_slow<COUNT>(sc, sv.sph, sv.sph2, i + 8, min(8, ns - i - 8), o, d, weird, best, ctr);
+            if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(hc, sv.sph, sv.sph2, i, min(8, ns - i), o, d, weird, best, ctr);
+            if ((!(m1 < 0.0f) || weird) && i + 8 < ns) brute_group_slow<COUNT>(hc, sv.sph, sv.sph2, i + 8, min(8, ns - i - 8), o, d, weird, best, ctr);
         }
     }
     if (i < ns8) {
@@ -331,7 +365,7 @@ __device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView&
 #pragma unroll
         for (int k = 0; k < 4; k++) m0 = pair_margin((i >> 1) + k, m0);
         if (COUNT) ctr.v[CTR_SPH_TEST] += ns - i;
-        if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(sc, sv.sph, sv.sph2, i, ns - i, o, d, weird, best, ctr);
+        if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(hc, sv.sph, sv.sph2, i, ns - i, o, d, weird, best, ctr);
     }
     const int nt = (int)sc.nt;
     for (int j = 0; j < nt; j++) test_triangle<COUNT>(sc, sv.tri, j, ns + j, o, d, best, ctr);
@@ -376,10 +410,9 @@ __device__ __forceinline__ uint32_t quantise(float sum, float spp_f) {
 // ---------------------------------------------------------------------------------------------
 constexpr int TR_DONE = (int)0x80000000;  // traversal finished (never a leaf code: first_pid < 2^26)
 template <bool COUNT, bool WITH_BIG = true>
-__device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
+__device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
     best.pid = -1;
     best.dist = 0.0f;
-    best.unsure = false;
     // FILTER-domain ray constants; |1/d| is clamped so 0*inf never produces NaN slabs
     const float BIG = 1e30f;
     float ix = fminf(fmaxf(__frcp_rn(d.x), -BIG), BIG);
@@ -393,23 +426,19 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
     // rounding of the o-term: <= 3 * 2^-24 * |o*inv| per axis, in t (the c- and h-terms are padded on the host)
     const float slack = 4.8e-7f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 1e-30f;
     float cull = 1001.0f;  // a hit has t < T_MAX and length(p-o) ~ t
-    int stack[MAX_STACK + 1];
-    stack[0] = TR_DONE;  // sentinel: popping it ends the traversal, so a pop needs no emptiness test
-    int* top = stack + 1;  // next free entry
-    int cur = sc.lroot;
     const int ns = (int)sc.ns;
-    // split layout: the large primitives first (their hits shorten everything that follows)
-    for (uint32_t i = 0; WITH_BIG && i < sc.nbig; i++) {
-        const int pid = (int)sc.big_pid[i];
-        if (pid < ns) {
-            test_sphere<COUNT>(sc, sv.sph[pid], pid, o, d, best, ctr);
-        } else {
-            if (COUNT) ctr.v[CTR_TRI_TEST]++;
-            if (triangle_filter(sv.tri, pid - ns, o, d, cull)) triangle_exact<COUNT>(sc, sv.tri, pid - ns, pid, o, d, best, ctr);
-        }
-        if (best.pid >= 0) cull = fmaf(best.dist, 1.00001f, 1e-6f);
-    }
-    if (!sc.ltree) return;
+    const HitCtx hc = hit_ctx(sc);
+    // The stack starts as: sentinel | tree root | leaf codes of the big primitives (split layout), first one on top.
+    // The big primitives are therefore popped and tested before the tree is entered (their hits shorten everything that
+    // follows) by the SAME leaf code as every other primitive: the exact arithmetic exists once in the kernel, which
+    // matters because this kernel's working set of instructions sits at the edge of the instruction cache.
+    int stack[MAX_STACK + 1 + MAX_BIG];
+    stack[0] = TR_DONE;  // popping the sentinel ends the traversal, so a pop needs no emptiness test
+    int* top = stack + 1;  // next free entry
+    if (sc.ltree) *top++ = sc.lroot;
+#pragma unroll 1
+    for (int i = (int)sc.nbig - 1; WITH_BIG && i >= 0; i--) *top++ = __ldg(&sc.big_code[i]);
+    int cur = *--top;
     for (;;) {
         while (cur >= 0) {
             const float4* nrec = sv.na + 3 * cur;
@@ -433,21 +462,60 @@ __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView
             cur = nxt;
         }
         if (cur == TR_DONE) return;
-        // leaf = contiguous pid range of one kind: code = ~((first << 5) | (count - 1))
-        const int first = (~cur) >> 5, count = ((~cur) & 31) + 1;
-        if (first < ns) {
-            for (int i = 0; i < count; i++) test_sphere<COUNT>(sc, sv.sph[first + i], first + i, o, d, best, ctr);
+        // leaf = one primitive: code = ~(pid << 5).  FILTER first, then the reference's arithmetic for the root, then ONE
+        // consider() for both kinds.
+        const int pid = (~cur) >> 5;
+        float t = 0.0f;
+        bool cand = false;
+        if (pid < ns) {
+            const float4 s = sv.sph[pid];
+            // oc = origin - center is a single exact subtraction: shared by filter and exact path
+            const V3 oc = mk(x_sub(o.x, s.x), x_sub(o.y, s.y), x_sub(o.z, s.z));
+            // FILTER: the reference's discriminant is 4*(bh*bh - (|oc|^2 - r^2)), bh = d.oc.  Evaluated with FMAs, rejected
+            // only when negative by more than a generous rounding bound (~300 ulp of |oc|^2), or when both roots lie
+            // behind the origin (ray points away, origin outside): cannot be in [T_MIN, T_MAX)
+            const float bh = fmaf(oc.z, d.z, fmaf(oc.y, d.y, oc.x * d.x));
+            const float oc2 = fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x));
+            const float cf = oc2 - s.w;
+            const float disc = fmaf(bh, bh, -cf);
+            if (COUNT) ctr.v[CTR_SPH_TEST]++;
+            if (!(fmaf(oc2, 2e-5f, disc) < 0.0f) && !(bh > 0.0f && cf > 1e-4f * oc2)) {
+                if (COUNT) ctr.v[CTR_SPH_EXACT]++;
+                cand = sphere_root_exact(d, oc, s.w, &t);
+                if (COUNT && cand) ctr.v[CTR_SPH_HIT]++;
+            }
         } else {
-            for (int i = 0; i < count; i++) {
-                const int pid = first + i;
-                if (COUNT) ctr.v[CTR_TRI_TEST]++;
-                if (triangle_filter(sv.tri, pid - ns, o, d, cull)) triangle_exact<COUNT>(sc, sv.tri, pid - ns, pid, o, d, best, ctr);
+            if (COUNT) ctr.v[CTR_TRI_TEST]++;
+            if (triangle_filter(sv.tri, pid - ns, o, d, cull)) {
+                const V3 a = ld3(sv.tri[4 * (pid - ns) + 0]), ab = ld3(sv.tri[4 * (pid - ns) + 1]), ac = ld3(sv.tri[4 * (pid - ns) + 2]);
+                int stage;
+                cand = triangle_root_exact(o, d, a, ab, ac, &t, &stage);
+                if (COUNT) {
+                    if (stage >= 1) ctr.v[CTR_TRI_S1]++;
+                    if (stage >= 2) ctr.v[CTR_TRI_S2]++;
+                    if (stage >= 3) ctr.v[CTR_TRI_S3]++;
+                    if (cand) ctr.v[CTR_TRI_HIT]++;
+                }
             }
         }
-        if (best.pid >= 0) cull = fmaf(best.dist, 1.00001f, 1e-6f);
+        if (cand) {
+            consider(hc, o, d, t, pid, best);
+            cull = fmaf(best.dist, 1.00001f, 1e-6f);
+        }
         cur = *--top;
-        if (cur == TR_DONE) return;
     }
+}
+
+// The queries as the kernels call them: the nearest hit, with Hit::unsure resolved out of the pid bit it travelled in.
+template <bool COUNT>
+__device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
+    trace_brute_impl<COUNT>(sc, sv, o, d, best, ctr);
+    hit_finish(best);
+}
+template <bool COUNT, bool WITH_BIG = true>
+__device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
+    trace_bvh_ch_impl<COUNT, WITH_BIG>(sc, sv, o, d, best, ctr);
+    hit_finish(best);
 }
 
 }  // namespace rtb

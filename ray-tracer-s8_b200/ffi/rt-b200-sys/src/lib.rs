@@ -59,7 +59,11 @@ pub struct rt_params {
     pub focal_length: f32,
     pub intersector: u32,
     pub collect_counters: u32,
+    /// `RT_PARAM_*`: fields whose zero is a value, not "the reference's literal"
+    pub flags: u32,
 }
+pub const RT_PARAM_MAX_BOUNCES_EXPLICIT: u32 = 1;
+pub const RT_PARAM_APERTURE_EXPLICIT: u32 = 2;
 
 #[repr(C)]
 #[derive(Clone, Copy, Debug, Default)]
@@ -88,7 +92,7 @@ pub struct rt_stats {
     pub ctas_per_sm: u32,
     pub scene_in_smem: u32,
     pub dyn_smem_bytes: u32,
-    pub reserved0: u32,
+    pub redo_pixels: u32,
 }
 
 extern "C" {
@@ -118,6 +122,16 @@ extern "C" {
     pub fn rt_render_frame(
         ctx: *mut rt_ctx,
         scene: *const rt_scene,
+        params: *const rt_params,
+        out_rgb: *mut u8,
+        out_len: usize,
+        stats: *mut rt_stats,
+    ) -> c_int;
+    pub fn rt_scene_wait_ready(ctx: *mut rt_ctx, scene: *const rt_scene) -> c_int;
+    pub fn rt_render_frame_multi(
+        ctxs: *const *mut rt_ctx,
+        scenes: *const *const rt_scene,
+        n: u32,
         params: *const rt_params,
         out_rgb: *mut u8,
         out_len: usize,
@@ -193,6 +207,15 @@ impl Context {
 
     /// `world_index[i]` = position of primitive i (spheres first, then triangles) in the `Vec<Object>`.
     pub fn scene(&self, spheres: &[rt_sphere], triangles: &[rt_triangle], world_index: Option<&[u32]>) -> Result<Scene<'_>, Error> {
+        if let Some(w) = world_index {
+            // the C side reads n_spheres + n_triangles entries
+            if w.len() != spheres.len() + triangles.len() {
+                return Err(Error {
+                    status: -1,
+                    message: format!("world_index has {} entries for {} primitives", w.len(), spheres.len() + triangles.len()),
+                });
+            }
+        }
         let mut raw = ptr::null_mut();
         let wi = world_index.map_or(ptr::null(), |w| w.as_ptr());
         let rc = unsafe {
@@ -212,6 +235,20 @@ impl Context {
         self.check(rc)?;
         Ok(out)
     }
+}
+
+/// One frame over several GPUs from this process (`rt_render_frame_multi`): `ctxs[i]` renders rank i's share of the
+/// 8x4 tiles of `scenes[i]` (the same world uploaded on that context) straight into `ctxs[0]`'s frame over NVLink; the
+/// frame streams to the returned buffer while it renders.  This is the controller's fan-out + stitch
+/// (ray-tracer-controller/src/main.rs:47-75,109-119) without HTTP.
+pub fn render_frame_multi(ctxs: &[&Context], scenes: &[&Scene<'_>], params: &rt_params) -> Result<Vec<u8>, Error> {
+    assert!(!ctxs.is_empty() && ctxs.len() == scenes.len(), "one scene per context");
+    let c: Vec<*mut rt_ctx> = ctxs.iter().map(|c| c.raw).collect();
+    let s: Vec<*const rt_scene> = scenes.iter().map(|s| s.raw as *const rt_scene).collect();
+    let mut out = vec![0u8; params.height as usize * params.width as usize * 3];
+    let rc = unsafe { rt_render_frame_multi(c.as_ptr(), s.as_ptr(), c.len() as u32, params, out.as_mut_ptr(), out.len(), ptr::null_mut()) };
+    ctxs[0].check(rc)?;
+    Ok(out)
 }
 
 impl Drop for Context {

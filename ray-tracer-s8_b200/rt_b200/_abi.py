@@ -12,7 +12,9 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 LIB_DIR = os.path.normpath(os.path.join(PKG_DIR, "..", "lib"))
 # RT_B200_LIB=exp selects the experiments build (product + the A/B kernels of csrc/experiments/, `make exp`): tooling and
 # the variant-agreement test only.  The product library is the default and carries no A/B code.
-LIB_PATH = os.path.join(LIB_DIR, "librt_b200_exp.so" if os.environ.get("RT_B200_LIB") == "exp" else "librt_b200.so")
+_sel = os.environ.get("RT_B200_LIB", "")
+LIB_PATH = (_sel if "/" in _sel else           # a development build under another name (A/B measurements)
+            os.path.join(LIB_DIR, "librt_b200_exp.so" if _sel == "exp" else "librt_b200.so"))
 
 RT_OK = 0
 RT_ERR_INVALID_ARG = -1

@@ -4,9 +4,13 @@
   POST /result               body = ImageSlice JSON        → "slice saved. thank you slave."   (main.rs:79-93)
   POST /poll                 body = job id                 → JPEG(90) | status text   (main.rs:95-142)
 
-Same literals as the reference: 1920x1080, 20 divisions (main.rs:33-36), the same status strings.  Dispatch is
-either the reference's (HTTP `RenderInfo` POSTs to `http://slave:8081`, results arrive on /result) or in-process
-(`worker=`): the 20 divisions of a job are rendered by one `rt_b200.slave.Worker`, which uploads the scene once.
+Same literals as the reference: 1920x1080, 20 divisions (main.rs:33-36), the same status strings.  Dispatch is one of
+  * the reference's: HTTP `RenderInfo` POSTs to `http://slave:8081`, results arrive on /result (main.rs:47-75);
+  * `worker=`: the divisions of a job are rendered in-process by one `rt_b200.slave.Worker` (one GPU, scene uploaded once);
+  * `devices=[...]`: the tile scheduler — the whole frame in ONE call over all listed GPUs (`rt_render_frame_multi`:
+    every GPU renders an interleaved share of the 8x4 tiles straight into GPU 0's frame over NVLink), then cut into
+    the job's divisions so /poll stitches them exactly as it stitches slave slices (main.rs:109-119).
+GPU work from concurrent /upload requests is serialised (one rt_ctx has one owner at a time).
 """
 from __future__ import annotations
 
@@ -27,11 +31,39 @@ SAVED_TEXT = "slice saved. thank you slave."       # main.rs:92
 
 
 class Controller:
-    def __init__(self, worker=None, slave_url: str = SLAVE_URL, width=WIDTH, height=HEIGHT, divisions=DIVISIONS):
+    def __init__(self, worker=None, slave_url: str = SLAVE_URL, width=WIDTH, height=HEIGHT, divisions=DIVISIONS,
+                 devices=None, spp: int = 0, max_bounces: int = 0, seed: int = 0):
         self.worker, self.slave_url = worker, slave_url
         self.width, self.height, self.divisions = width, height, divisions
         self.jobs: dict = {}          # id → {"meta": RenderMeta, "result": {division_no: uint8 array}}
         self.lock = threading.Lock()
+        self.gpu_lock = threading.Lock()   # the multi-GPU renderer's contexts: one frame at a time
+        self.multi = None
+        self.spp, self.max_bounces, self.seed = spp, max_bounces, seed
+        if devices is not None:
+            from . import multi
+
+            self.multi = multi.MultiDeviceRenderer(list(devices))
+
+    def close(self):
+        if self.multi is not None:
+            self.multi.close()
+            self.multi = None
+
+    def _render_all_gpus(self, triangles, meta: "wire.RenderMeta"):
+        """devices= mode: one frame over all GPUs, returned as the job's division slices."""
+        from . import api
+
+        p = api.make_params(meta.width, meta.height, spp=self.spp, max_bounces=self.max_bounces, seed=self.seed)
+        with self.gpu_lock:
+            scenes = self.multi.scenes(None, triangles, np.arange(len(triangles), dtype=np.uint32))
+            try:
+                frame = self.multi.render(scenes, p)
+            finally:
+                for sc in scenes:
+                    sc.close()
+        rows = meta.height // meta.divisions          # main.rs:55-56
+        return [wire.ImageSlice(d, frame[d * rows:(d + 1) * rows].reshape(-1), meta.id) for d in range(meta.divisions)]
 
     # -- /upload ---------------------------------------------------------------------------------------
     def upload(self, body: bytes, obj_size: int) -> str:
@@ -40,7 +72,12 @@ class Controller:
         with self.lock:
             self.jobs[job_id] = {"meta": meta, "result": {}}
         triangles = objmod.build_world(body, obj_size)          # obj::build_world (main.rs:46)
-        if self.worker is not None:
+        if self.multi is not None:
+            if self.height % self.divisions != 0:
+                raise ValueError(f"height {self.height} is not a multiple of divisions {self.divisions}")
+            for sl in self._render_all_gpus(triangles, meta):
+                self.result(sl)
+        elif self.worker is not None:
             world = wire.World(np.zeros(0, wire.SPHERE_DTYPE), triangles, np.arange(len(triangles), dtype=np.uint32))
             for d in range(self.divisions):
                 self.result(self.worker.render(wire.RenderInfo(world, meta, d)))

@@ -15,6 +15,7 @@ from __future__ import annotations
 import queue
 import threading
 import urllib.request
+import zlib
 from collections import OrderedDict
 from http.server import BaseHTTPRequestHandler, ThreadingHTTPServer
 
@@ -34,12 +35,27 @@ class Worker:
                  intersector: int = api.INTERSECT_AUTO):
         self.ctx = api.Context(device)
         self.spp, self.max_bounces, self.seed, self.intersector = spp, max_bounces, seed, intersector
-        self._scenes: "OrderedDict[str, api.Scene]" = OrderedDict()
+        self._scenes: "OrderedDict[tuple, api.Scene]" = OrderedDict()
         self._cache_size = cache_size
         self.scene_uploads = 0
+        # one rt_ctx = one owner at a time (include/rt_b200.h): callers on several threads (the controller's in-process
+        # mode under a threading HTTP server) are serialised here
+        self.lock = threading.Lock()
+
+    @staticmethod
+    def _world_key(info: wire.RenderInfo):
+        """Job id + a checksum of the world: every RenderInfo carries its own world (lib.rs:25-30), so a client that
+        reuses an id with other geometry must not get the cached scene."""
+        w = info.world
+        crc = 0
+        for a in (w.spheres, w.triangles, w.world_index):
+            if a is not None and len(a):
+                crc = zlib.crc32(np.ascontiguousarray(a).view(np.uint8).reshape(-1), crc)
+        return (info.render_meta.id, 0 if w.spheres is None else len(w.spheres),
+                0 if w.triangles is None else len(w.triangles), crc)
 
     def _scene_for(self, info: wire.RenderInfo) -> api.Scene:
-        key = info.render_meta.id
+        key = self._world_key(info)
         sc = self._scenes.get(key)
         if sc is None:
             w = info.world
@@ -57,7 +73,8 @@ class Worker:
         m = info.render_meta
         p = api.make_params(m.width, m.height, divisions=m.divisions, division_no=info.division_no, spp=self.spp,
                             max_bounces=self.max_bounces, seed=self.seed, intersector=self.intersector)
-        out = self.ctx.render_division(self._scene_for(info), p, want_stats=want_stats)
+        with self.lock:
+            out = self.ctx.render_division(self._scene_for(info), p, want_stats=want_stats)
         img, st = out if want_stats else (out, None)
         sl = wire.ImageSlice(info.division_no, np.ascontiguousarray(img).reshape(-1), m.id)
         return (sl, st) if want_stats else sl

@@ -23,6 +23,9 @@ BOTH = [1, 2]  # RT_INTERSECT_BRUTE, RT_INTERSECT_BVH
 def _render(ctx, rt, sp, tr, w, h, spp, mb, isect=0, seed=0, wi=None, **cam):
     sc = ctx.scene(sp, tr, wi)
     try:
+        # counters are compared with the oracle's below: have the tie-break tables first, so that no pixel is traced a
+        # second time (test_render_before_tables_land covers the path without this wait)
+        sc.wait_ready()
         p = rt.make_params(w, h, spp=spp, max_bounces=mb, seed=seed, intersector=isect, **cam)
         return ctx.render_frame(sc, p, want_stats=True)
     finally:
@@ -251,6 +254,209 @@ def test_counters_match_oracle(ctx, rt, O):
     sc.close()
 
 
+def test_c4_crop(ctx, rt, O):
+    """BASELINE config 4 (7680x4320, 4 spp, max_bounces 8, 1024 spheres + plane): one 10-row band of the 432 the tile
+    scheduler's configuration cuts the frame into, at the height where spheres, plane and sky meet."""
+    c = rt.scenes.CONFIGS["C4"]
+    sp, tr = rt.scenes.config_scene("C4")
+    div, d = c["height"] // 10, 2400 // 10
+    ref, ost = O.render_rows(sp, tr, O.make_params(c["width"], c["height"], div, d, c["spp"], c["max_bounces"]),
+                             want_stats=True)
+    sc = ctx.scene(sp, tr).wait_ready()
+    p = rt.make_params(c["width"], c["height"], divisions=div, division_no=d, spp=c["spp"], max_bounces=c["max_bounces"])
+    img, st = ctx.render_division(sc, p, want_stats=True)
+    sc.close()
+    assert img.shape == (10, 7680, 3)
+    assert_parity(img, ref)
+    assert st["rays"] == ost["rays"]
+
+
+def test_c5_65536_spheres_band(ctx, rt, O):
+    """BASELINE config 5's upper end: 65,536 spheres at 1080p, 1 spp, max_bounces 5 — scene read through L1/L2,
+    traversal tree built on the device, reference tree built beside the upload.  One of the controller's 20 bands."""
+    sp = rt.scenes.synthetic_spheres(65536)
+    ref, ost = O.render_rows(sp, None, O.make_params(1920, 1080, 20, 10, 1, 5), want_stats=True)
+    sc = ctx.scene(sp, None)
+    p = rt.make_params(1920, 1080, divisions=20, division_no=10, spp=1, max_bounces=5)
+    img, st = ctx.render_division(sc, p, want_stats=True)          # straight after the upload: tables may still be on their way
+    assert_parity(img, ref)
+    assert st["scene_in_smem"] == 0 and st["intersector_used"] == 2
+    sc.wait_ready()
+    img2, st2 = ctx.render_division(sc, p, want_stats=True)
+    sc.close()
+    assert np.array_equal(img, img2) and st2["rays"] == ost["rays"] and st2["redo_pixels"] == 0
+
+
+AXIS_CASES = [
+    # camera origin: on box planes of several spheres at once / strictly inside boxes / outside everything in x
+    (0.5, 0.25, 3.0), (0.5, 1.0, 3.0), (0.0, 0.25, 3.0), (0.75, 0.3, 3.0), (-3.0, 0.25, 3.0),
+]
+
+
+@pytest.mark.parametrize("isect", BOTH)
+@pytest.mark.parametrize("org", AXIS_CASES)
+def test_axis_aligned_rays_nan_slabs(ctx, rt, O, isect, org):
+    """Ray::intersects_aabb with a zero direction component (ray.rs:133-143,174-194 and the crate's min/max, ray.rs:82-112):
+    1/0 = inf and 0*inf = NaN planes.  A denormal field of view and aperture make EVERY primary ray exactly
+    (+0, +0, -1) from the camera origin, which sits on the min/max planes of several spheres' (and their ancestors')
+    boxes; a mirror wall sends the rays back as (0, 0, +1).  The reference's traversal drops or keeps subtrees by NaN
+    propagation order; the GPU path has to reproduce it (exact test on the shape's box + the ancestor chain of the
+    reference tree for such rays)."""
+    sc_ = rt.scenes
+    sp = np.zeros(12, dtype=sc_.SPHERE_DTYPE)
+    centers = [(1.5, 0.25, -4.0), (-0.5, 0.25, -6.0), (0.5, 1.25, -8.0), (0.5, -0.75, -2.0), (1.0, 0.75, -5.0),
+               (0.5, 0.25, -9.0), (2.5, 0.25, -3.0), (0.25, 0.0, -7.0), (-1.5, 1.25, -4.5), (0.75, 0.5, -1.0),
+               (0.5, 0.25, -12.0), (3.0, 3.0, -6.0)]
+    radii = [1.0, 1.0, 1.0, 1.0, 0.5, 0.25, 2.0, 0.25, 1.0, 0.25, 0.5, 1.0]
+    for i, (c, r) in enumerate(zip(centers, radii)):
+        sp[i] = (c, r, (0.9, 0.6 + 0.03 * i, 0.3), [0.0, 1.0, 0.5][i % 3], 2.0 if i == 11 else 0.0)
+    tr = np.zeros(2, dtype=sc_.TRIANGLE_DTYPE)   # mirror wall at z = -14 facing the camera
+    tr[0] = ((-20, -20, -14), (20, -20, -14), (20, 20, -14), (0.9, 0.9, 0.9), 1.0, 0.0)
+    tr[1] = ((-20, -20, -14), (20, 20, -14), (-20, 20, -14), (0.9, 0.9, 0.9), 1.0, 0.0)
+    cam = dict(cam_origin=org, aperture=1e-40, field_of_view=1e-40, focus_distance=1.0)
+    ref, ost = O.render_frame(sp, tr, 16, 8, 6, 6, seed=3, want_stats=True, **cam)
+    img, st = _render(ctx, rt, sp, tr, 16, 8, 6, 6, isect, seed=3, **cam)
+    assert_parity(img, ref)
+    assert st["rays"] == ost["rays"]
+    # and with the tables still on their way: every pixel depends on them, the second pass has to put it right
+    sc = ctx.scene(sp, tr)
+    img2 = ctx.render_frame(sc, rt.make_params(16, 8, spp=6, max_bounces=6, seed=3, intersector=isect, **cam))
+    sc.close()
+    assert np.array_equal(img2, ref)
+
+
+def _tie_mesh(rt, n_quads=160):
+    """Every triangle twice: each hit is an exact-distance tie that only the reference tree's leaf order decides
+    (shapes/mod.rs:177-182); the two copies differ in colour, so a wrong winner shows."""
+    rng = np.random.default_rng(5)
+    tr = np.zeros(4 * n_quads, dtype=rt.scenes.TRIANGLE_DTYPE)
+    for q in range(n_quads):
+        c = np.array([rng.uniform(-6, 6), rng.uniform(-3.5, 3.5), rng.uniform(-14, -5)], dtype=np.float32)
+        e1 = rng.normal(size=3).astype(np.float32) * 0.9
+        e2 = rng.normal(size=3).astype(np.float32) * 0.9
+        if q == 0:  # a wall behind everything that fills the view: no pixel without a tie
+            c = np.array([-60, -40, -20], dtype=np.float32)
+            e1, e2 = np.array([120, 0, 0], dtype=np.float32), np.array([0, 80, 0], dtype=np.float32)
+        a, b, cc, dd = c, c + e1, c + e1 + e2, c + e2
+        for k, (p0, p1, p2) in enumerate(((a, b, cc), (a, cc, dd))):
+            tr[4 * q + 2 * k] = (p0, p1, p2, (0.9, 0.2, 0.2), 0.3, 0.0)
+            tr[4 * q + 2 * k + 1] = (p0, p1, p2, (0.2, 0.2, 0.9), 0.3, 0.0)
+    return tr
+
+
+def test_render_before_tables_land(rt, O):
+    """rt_scene_create returns before the reference-topology tree is built (its tables only break exact-distance ties).
+    RT_B200_AUX_DELAY_MS holds the builder thread back, so the first frame is rendered without the tables for certain:
+    the kernel must mark every tie pixel and the second pass must reproduce the oracle's frame — with a pixel list
+    (few ties) and by repeating the launch (more tie pixels than the list holds)."""
+    import os
+    import subprocess
+    import sys
+    import hashlib
+
+    code = (
+        "import sys, hashlib, numpy as np; sys.path.insert(0, 'ray-tracer-s8_b200'); sys.path.insert(0, 'tests');"
+        "import rt_b200 as rt; from test_gpu_parity import _tie_mesh;"
+        "ctx = rt.Context(0); tr = _tie_mesh(rt); out = [];\n"
+        "for (w, h) in ((96, 64), (512, 320)):\n"
+        "    sc = ctx.scene(None, tr)\n"
+        "    img, st = ctx.render_frame(sc, rt.make_params(w, h, spp=2, max_bounces=3, seed=7), want_stats=True)\n"
+        "    out.append(hashlib.sha256(img.tobytes()).hexdigest() + ':' + str(st['redo_pixels'])); sc.close()\n"
+        "print(' '.join(out))"
+    )
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    env = dict(os.environ, RT_B200_AUX_DELAY_MS="300")
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-800:]
+    got = out.stdout.strip().splitlines()[-1].split()
+    tr = _tie_mesh(rt)
+    for (w, h), g in zip(((96, 64), (512, 320)), got):
+        ref, _ = O.render_frame(None, tr, w, h, 2, 3, seed=7)
+        digest, redo = g.split(":")
+        assert digest == hashlib.sha256(ref.tobytes()).hexdigest(), (w, h, redo)
+        assert int(redo) > 0, "the first pass must have met ties without the tables"
+    assert int(got[0].split(":")[1]) < 65536 and int(got[1].split(":")[1]) == 0xffffffff
+
+
+def test_pinhole_and_zero_bounce_flags(ctx, rt, O):
+    """rt_params.flags: aperture 0 = pinhole and max_bounces 0 = camera rays only, instead of the reference's literals."""
+    sp, tr = rt.scenes.synthetic_spheres(40, 9), rt.scenes.ground_plane()
+    sc = ctx.scene(sp, tr).wait_ready()
+    a = ctx.render_frame(sc, rt.make_params(96, 64, spp=2, max_bounces=0, aperture=0.0, explicit=("max_bounces", "aperture")))
+    b, sb = ctx.render_frame(sc, rt.make_params(96, 64, spp=2, max_bounces=0, aperture=0.0), want_stats=True)   # literals: 10, 0.1
+    c, sc_st = ctx.render_frame(sc, rt.make_params(96, 64, spp=2, max_bounces=0, explicit=("max_bounces",)), want_stats=True)
+    sc.close()
+    assert sc_st["rays"] == 96 * 64 * 2 and sb["rays"] > sc_st["rays"]      # one query per sample
+    ref, _ = O.render_frame(sp, tr, 96, 64, 2, 0)
+    assert_parity(b, ref)
+    assert not np.array_equal(a, c)                                         # pinhole vs aperture 0.1
+    # every hit pixel of a camera-rays-only frame is black unless the hit emits: paths end after one query
+    assert (c.reshape(-1, 3).max(axis=1) == 0).mean() > 0.05
+
+
+def test_multi_context_frame_matches_single(ctx, rt, O):
+    """rt_render_frame_multi: N contexts (here on one device; see the 2-device test) render interleaved tile shares
+    into context 0's frame; the frame equals the single-context frame and the oracle's."""
+    from rt_b200 import multi
+
+    sp, tr = rt.scenes.synthetic_spheres(200, 6), rt.scenes.ground_plane()
+    ref, ost = O.render_frame(sp, tr, 322, 181, 3, 5, seed=2, want_stats=True)
+    p = rt.make_params(322, 181, spp=3, max_bounces=5, seed=2)
+    m = multi.MultiDeviceRenderer([0, 0, 0])
+    try:
+        scenes = [s.wait_ready() for s in m.scenes(sp, tr)]
+        img, st = m.render(scenes, p, want_stats=True)
+        for s in scenes:
+            s.close()
+    finally:
+        m.close()
+    assert_parity(img, ref)
+    assert st["rays"] == ost["rays"] and st["primary"] == 322 * 181 * 3 and st["kernel_launches"] == 3
+
+
+def test_two_devices_p2p_and_nccl(rt, O):
+    """Two GPUs: (a) one process, rt_render_frame_multi over peer access; (b) bench.py under torchrun, one process per
+    GPU, frame assembled by peer stores (p2p) and by NCCL — all must produce the single-GPU frame (same sha256)."""
+    import json
+    import os
+    import subprocess
+    import sys
+
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    from rt_b200 import multi
+
+    c = rt.scenes.CONFIGS["C2"]
+    sp, tr = rt.scenes.config_scene("C2")
+    p = rt.make_params(c["width"], c["height"], spp=2, max_bounces=c["max_bounces"])
+    with rt.Context(0) as c0:
+        sc = c0.scene(sp, tr)
+        one = c0.render_frame(sc, p)
+        sc.close()
+    m = multi.MultiDeviceRenderer([0, 1])
+    try:
+        scenes = m.scenes(sp, tr)
+        two, st = m.render(scenes, p, want_stats=True)
+        for s in scenes:
+            s.close()
+    finally:
+        m.close()
+    assert np.array_equal(one, two)
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    hashes = {}
+    for mode, gpus in (("single", 1), ("p2p", 2), ("nccl", 2)):
+        cmd = [sys.executable, os.path.join(root, "bench.py"), "--gpus", str(gpus), "--steps", "2", "--warmup", "3",
+               "--workload", "C2", "--no-cpu-baseline"] + (["--mode", mode] if gpus > 1 else [])
+        out = subprocess.run(cmd, cwd=root, capture_output=True, text=True, timeout=900)
+        assert out.returncode == 0, (mode, out.stderr[-800:])
+        line = json.loads(out.stdout.strip().splitlines()[-1])
+        hashes[mode] = line["frame_sha256"]
+        assert line["n_gpus"] == gpus
+    assert len(set(hashes.values())) == 1, hashes
+
+
 # ---------------------------------------------------------------------------------------------------
 # size-independent properties at BASELINE's full sizes
 # ---------------------------------------------------------------------------------------------------
@@ -304,7 +510,7 @@ def test_error_codes(ctx, rt):
     assert e.value.status == -2 and "never terminates" in e.value.message
     sc = ctx.scene(sp, None)
     with pytest.raises(rt.RtError) as e:
-        ctx.render_frame(sc, rt.make_params(16, 9, divisions=2, spp=1, max_bounces=1))
+        ctx.render_division(sc, rt.make_params(16, 9, divisions=2, spp=1, max_bounces=1))
     assert e.value.status == -1 and "multiple of divisions" in e.value.message
     with pytest.raises(rt.RtError) as e:
         ctx.render_frame(sc, rt.make_params(16, 8, spp=1, max_bounces=1), out=np.zeros((8, 16, 2), dtype=np.uint8))

@@ -18,14 +18,14 @@ def main():
                                           ("p3", 101, 67, 3, 4, 32, True), ("p4", 64, 48, 2, 5, 1, False)]:
         sp = scenes.synthetic_spheres(n, 3); tr = scenes.ground_plane() if plane else None
         ref, ost = O.render_frame(sp, tr, w, h, spp, mb, want_stats=True)
-        sc = ctx.scene(sp, tr)
+        sc = ctx.scene(sp, tr).wait_ready()
         img, st = ctx.render_frame(sc, rt.make_params(w, h, spp=spp, max_bounces=mb, intersector=2), want_stats=True)
         sc.close()
         print(name, "ndiff", int((img != ref).sum()), "rays", st["rays"], ost["rays"])
     for name in names:
         cfg = scenes.CONFIGS[name]
         sp, tr = scenes.config_scene(name)
-        sc = ctx.scene(sp, tr)
+        sc = ctx.scene(sp, tr).wait_ready()
         for isect in (1, 2):
             if isect == 1 and cfg["n_spheres"] > 300:
                 continue

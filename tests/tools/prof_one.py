@@ -10,7 +10,7 @@ reps = int(sys.argv[3]) if len(sys.argv) > 3 else 3
 cfg = scenes.CONFIGS[name]
 sp, tr = scenes.config_scene(name)
 ctx = rt.Context(0)
-sc = ctx.scene(sp, tr)
+sc = ctx.scene(sp, tr).wait_ready()
 p = rt.make_params(cfg["width"], cfg["height"], spp=cfg["spp"], max_bounces=cfg["max_bounces"], intersector=isect)
 for _ in range(reps):
     img, st = ctx.render_frame(sc, p, want_stats=True)
