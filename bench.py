@@ -10,15 +10,23 @@ GPUs of one box, frame assembled on rank 0.  A ray = one nearest-hit query (ray_
   python bench.py --impl reference ...                    # the reference algorithm on the host cores (oracle port)
   python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
-One JSON line on stdout (rank 0).  `value` = whole-job Mrays/s with the scene resident in HBM and the frame
-left in HBM; `e2e` = the same through the C ABI with host buffers (scene upload + BVH build + render + frame
-download every step).
+One JSON line on stdout (rank 0).
+  value     whole-job Mrays/s, scene resident in HBM, frame left in HBM (on rank 0)
+  e2e       the same through the C ABI with HOST buffers: rt_scene_create (ingest + upload) + render + the frame in
+            host memory, every step
+  parity    the timed frame against the oracle bands the cpu_baseline leg renders (N = 1), and frame_sha256 of the
+            assembled frame at every N (the same hash at N = 1, 2, 4, 8 = the same bytes)
+  roofline  FP32 pipe: algorithmic FLOPs (SURVEY Appendix C x the kernel's own counters) / CUDA-event kernel time
+            against a live FFMA-chain peak; ncu figures are read from the summary file the line names
+  extra     (default run, N = 1) the other BASELINE configs: C2, C4 and the C5 sweep's ends
 """
 from __future__ import annotations
 
 import argparse
+import hashlib
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -33,7 +41,7 @@ import numpy as np  # noqa: E402
 
 METRIC = "Mrays/s"
 UNIT = "Mrays/s"
-
+FLUSH_BYTES = 160 << 20   # > 126 MB L2
 
 # --------------------------------------------------------------------------------------------------------
 # FLOP model (add/sub/mul/div/sqrt = 1, FMA = 2, compares/min/max/int = 0), applied to
@@ -119,16 +127,18 @@ def sample_divisions(k: int):
     return [int((i + 0.5) * REF_DIVISIONS / k) for i in range(k)]
 
 
-def oracle_sample(O, sp, tr, cfg, divs, threads=0):
+def oracle_sample(O, sp, tr, cfg, divs, threads=0, keep=None):
     """Render the given divisions with the oracle, each like one reference slave request (world ingest + BVH
-    build + band render, ray-tracer-slave/src/main.rs:37-83); returns (rays, seconds)."""
+    build + band render, ray-tracer-slave/src/main.rs:37-83); returns (rays, seconds).  keep: dict band → pixels."""
     rays, secs = 0, 0.0
     for d in divs:
         p = O.make_params(cfg["width"], cfg["height"], REF_DIVISIONS, d, cfg["spp"], cfg["max_bounces"], 0)
         t0 = time.perf_counter()
-        _, st = O.render_rows(sp, tr, p, threads=threads, want_stats=True)
+        img, st = O.render_rows(sp, tr, p, threads=threads, want_stats=True)
         secs += time.perf_counter() - t0
         rays += st["rays"]
+        if keep is not None:
+            keep[d] = img
     return rays, secs
 
 
@@ -150,12 +160,15 @@ def describe_sample(cfg, divs):
 
 
 def run_reference(args, cfg, sp, tr):
-    """--impl reference: the reference's CPU algorithm (oracle port, all host threads) on the same config."""
+    """--impl reference: the reference's CPU algorithm (oracle port, all host threads) on the same config.
+    A step is the whole frame (all 20 of the controller's divisions) whenever the run then still ends within a
+    few minutes on this box's cores; otherwise an evenly spaced subset, and the line says which fraction."""
     from oracle import oracle as O
 
     O.build()
     cores = O.hardware_threads()
-    divs = pick_sample(O, sp, tr, cfg, target_s=4.0)
+    budget_s = 170.0 / max(1, args.steps + args.warmup)        # per step
+    divs = pick_sample(O, sp, tr, cfg, target_s=budget_s)
     for _ in range(args.warmup):
         oracle_sample(O, sp, tr, cfg, divs[:1])
     rays, secs = 0, 0.0
@@ -164,28 +177,66 @@ def run_reference(args, cfg, sp, tr):
         rays += r
         secs += s
     val = rays / secs / 1e6
+    frac = len(divs) / REF_DIVISIONS
     sample = describe_sample(cfg, divs) + " per step"
-    line = {
+    return {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True, "scaling": "strong",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, cfg),
+        "frame_fraction_per_step": frac, "frame_ms_extrapolated": secs / args.steps * 1e3 / frac,
         "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample,
                          "note": "C++ oracle = operation-for-operation port of the Rust slave (reference BVH build + "
                                  "unordered traversal); omits the reference's per-ray heap allocations, so it flatters the CPU"},
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    return line
 
 
 def workload_config(args, cfg):
+    """The same keys and values in both arms (the driver compares them)."""
     return {"workload": f"{args.workload}: {cfg['width']}x{cfg['height']}, {cfg['spp']} spp, max_bounces {cfg['max_bounces']} "
                         f"(<= {cfg['max_bounces'] + 1} queries/sample), {cfg['n_spheres']} spheres"
                         + (" + plane (2 triangles)" if cfg["plane"] else "") + ", scene_seed 0, seed 0",
             "width": cfg["width"], "height": cfg["height"], "spp": cfg["spp"], "max_bounces": cfg["max_bounces"],
             "n_spheres": cfg["n_spheres"], "n_triangles": 2 if cfg["plane"] else 0,
-            "partition": f"8x4-pixel tiles, rotating interleave over {args.gpus} GPU(s)"}
+            "partition": f"8x4-pixel tiles, rotating interleave over {args.gpus} GPU(s)",
+            "l2": "flushed between steps: 160 MiB device memset queued in front of every frame"}
+
+
+def compare_frames(a, b):
+    """north_star tolerance: every channel within +-1 LSB on >= 99.9 % of pixels and PSNR >= 50 dB."""
+    d = np.abs(a.astype(np.int32) - b.astype(np.int32))
+    mse = float((d.astype(np.float64) ** 2).mean())
+    return {"n_diff": int((d > 0).sum()), "frac_within_1lsb": float((d.reshape(-1, 3).max(axis=-1) <= 1).mean()),
+            "psnr_db": None if mse == 0 else float(10.0 * np.log10(255.0 ** 2 / mse)), "max_diff": int(d.max())}
+
+
+def ncu_block(path):
+    """Pipe / issue figures of the dominant kernel from a committed ncu summary (profiles/); None if it is missing."""
+    full = os.path.join(ROOT, path)
+    if not os.path.exists(full):
+        return None
+    txt = open(full).read()
+
+    def grab(name):
+        m = re.search(re.escape(name) + r"\s+\S+\s+([0-9.eE+-]+)", txt)
+        return float(m.group(1)) if m else None
+
+    out = {"source": path,
+           "issue_slots_pct": grab("sm__inst_issued.avg.pct_of_peak_sustained_active"),
+           "fma_pipe_cycles_pct": grab("sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+           "alu_pipe_pct": grab("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+           "threads_per_warp_inst": grab("smsp__thread_inst_executed_per_inst_executed.ratio"),
+           "warp_inst": grab("smsp__inst_executed.sum"),
+           "kernel_ms": grab("gpu__time_duration.sum")}
+    rd, wr = grab("dram__bytes_read.sum"), grab("dram__bytes_write.sum")
+    m = re.search(r"dram__bytes_read\.sum\s+(\S+)", txt)
+    scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(m.group(1), None) if m else None
+    mw = re.search(r"dram__bytes_write\.sum\s+(\S+)", txt)
+    scale_w = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0}.get(mw.group(1), None) if mw else None
+    out["dram_bytes"] = (rd * scale + wr * scale_w) if None not in (rd, wr, scale, scale_w) else None
+    return out
 
 
 # --------------------------------------------------------------------------------------------------------
@@ -197,6 +248,45 @@ def _claim_stdout():
     return real
 
 
+def extra_workloads(rt, ctx, scenes):
+    """The other BASELINE configs on one GPU (default run only): kernel time, Mrays/s, e2e ms; C5 ends with ingest time."""
+    out = {}
+    for name in ("C2", "C4"):
+        cfg = scenes.CONFIGS[name]
+        sp, tr = scenes.config_scene(name)
+        sc = ctx.scene(sp, tr).wait_ready()
+        p = rt.make_params(cfg["width"], cfg["height"], spp=cfg["spp"], max_bounces=cfg["max_bounces"])
+        host = ctx.pinned_empty((cfg["height"], cfg["width"], 3))
+        ks, es = [], []
+        for i in range(6):
+            ctx.l2_flush(FLUSH_BYTES)
+            t0 = time.perf_counter()
+            _, st = ctx.render_frame(sc, p, out=host, want_stats=True)
+            es.append((time.perf_counter() - t0) * 1e3)
+            ks.append(st["kernel_ms"])
+        out[name] = {"kernel_ms": float(np.median(ks[1:])), "mrays_per_s": st["rays"] / np.median(ks[1:]) / 1e3,
+                     "render_plus_download_ms": float(np.median(es[1:])), "rays": st["rays"],
+                     "frame_sha256": hashlib.sha256(host.tobytes()).hexdigest()[:16]}
+        sc.close()
+    for n in (64, 65536):      # BASELINE config 5: the sweep's ends, 1080p, 1 spp, depth 5
+        sp = scenes.synthetic_spheres(n)
+        p = rt.make_params(1920, 1080, spp=1, max_bounces=5)
+        host = ctx.pinned_empty((1080, 1920, 3))
+        ing, ks, es = [], [], []
+        for i in range(4):
+            t0 = time.perf_counter()
+            sc = ctx.scene(sp, None)
+            t1 = time.perf_counter()
+            _, st = ctx.render_frame(sc, p, out=host, want_stats=True)
+            t2 = time.perf_counter()
+            sc.close()
+            ing.append((t1 - t0) * 1e3); ks.append(st["kernel_ms"]); es.append((t2 - t0) * 1e3)
+        out[f"C5_n{n}"] = {"scene_create_ms": float(np.median(ing[1:])), "kernel_ms": float(np.median(ks[1:])),
+                           "e2e_ms": float(np.median(es[1:])), "mrays_per_s": st["rays"] / np.median(ks[1:]) / 1e3,
+                           "redo_pixels": st["redo_pixels"]}
+    return out
+
+
 def main():
     real_stdout = _claim_stdout()
     ap = argparse.ArgumentParser()
@@ -205,9 +295,10 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C3")
-    ap.add_argument("--mode", default=os.environ.get("RT_B200_GATHER", "p2p"), choices=["p2p", "nccl"])
+    ap.add_argument("--mode", default=os.environ.get("RT_B200_GATHER", "p2p"), choices=["p2p", "nccl", "single"])
     ap.add_argument("--intersector", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
@@ -260,31 +351,25 @@ def main():
     torch.cuda.set_device(local_rank)
     ctx = rt.Context(local_rank)
     info = ctx.device_info()
-    scene = ctx.scene(sp, tr)
+    scene = ctx.scene(sp, tr).wait_ready()
     W, H = cfg["width"], cfg["height"]
     pixels = W * H
     params = rt.make_params(W, H, spp=cfg["spp"], max_bounces=cfg["max_bounces"], intersector=args.intersector)
 
-    sched = multi.FrameScheduler(ctx, rank, world, mode=args.mode)
-    gather_mode = args.mode if world > 1 else "none"
-    try:
-        sched.setup(W, H)
-    except rt.RtError as e:
-        if world > 1 and args.mode == "p2p":
-            raise RuntimeError(f"peer-mapped frame unavailable ({e}); rerun with --mode nccl") from e
-        raise
+    mode = args.mode if world > 1 else "single"
+    sched = multi.FrameScheduler(ctx, rank, world, mode=mode if world > 1 else "p2p")
+    sched.setup(W, H)
 
     # ---- counters for the roofline: one untimed instrumented frame (deterministic → same work as timed steps)
     pc = rt.make_params(W, H, spp=cfg["spp"], max_bounces=cfg["max_bounces"], intersector=args.intersector,
                         collect_counters=True)
     cst = sched.render(scene, pc, want_stats=True)
     fp32_peak_tflops, _ = ctx.measure_fp32_peak()
-
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=f"cuda:{local_rank}")  # > 126 MB L2
+    flush_ms = ctx.l2_flush(FLUSH_BYTES, timed=True)
+    flush_ms = min(flush_ms, ctx.l2_flush(FLUSH_BYTES, timed=True))
 
     def step():
-        flush.zero_()
-        torch.cuda.current_stream().synchronize()
+        ctx.l2_flush(FLUSH_BYTES)                      # asynchronous, on the render stream, in front of the kernel
         return sched.render(scene, params, want_stats=True)
 
     for _ in range(args.warmup):
@@ -310,18 +395,20 @@ def main():
     value = rays_total * args.steps / elapsed_max / 1e6
     ms_per_step = elapsed_max / args.steps * 1e3
 
-    # ---- e2e: through the C ABI with host buffers; scene upload (+BVH build) and frame download every step
+    # ---- e2e: through the C ABI with host buffers; scene ingest + upload, render, frame in host memory, every step
     host_frame = ctx.pinned_empty((H, W, 3)) if rank == 0 else None
     scene_bytes = scene.device_bytes
+    e2e_redo = 0
 
     def e2e_step():
-        sc = ctx.scene(sp, tr)                       # H2D: primitive SoA + BVH + materials
+        nonlocal e2e_redo
+        ctx.l2_flush(FLUSH_BYTES)
+        sc = ctx.scene(sp, tr)                       # H2D: primitive SoA + traversal tree + materials (tie tables follow)
         if world == 1:
-            ctx.render_frame(sc, params, out=host_frame)   # kernel + D2H of the frame
+            _, s1 = ctx.render_frame(sc, params, out=host_frame, want_stats=True)   # kernel + D2H of the frame
         else:
-            sched.render(sc, params)
-            if rank == 0:
-                sched.download(host_frame)
+            s1 = sched.render(sc, params, want_stats=True, out=host_frame)          # slabs stream to the host as they complete
+        e2e_redo = max(e2e_redo, s1["redo_pixels"])
         sc.close()
 
     for _ in range(2):
@@ -333,47 +420,70 @@ def main():
     barrier()
     e2e_elapsed = allreduce(time.perf_counter() - t0, ROp.MAX if ROp else None)
     e2e_value = rays_total * args.steps / e2e_elapsed / 1e6
+    frame_sha = hashlib.sha256(host_frame.tobytes()).hexdigest() if rank == 0 else None
+
+    # the same with a pageable destination (what a Rust Vec<u8> is): N = 1 only, a few steps
+    e2e_pageable_ms = None
+    if world == 1:
+        pageable = np.empty((H, W, 3), dtype=np.uint8)
+        ts = []
+        for _ in range(4):
+            ctx.l2_flush(FLUSH_BYTES)
+            t1 = time.perf_counter()
+            sc = ctx.scene(sp, tr)
+            ctx.render_frame(sc, params, out=pageable)
+            sc.close()
+            ts.append((time.perf_counter() - t1) * 1e3)
+        e2e_pageable_ms = float(np.median(ts[1:]))
+        assert hashlib.sha256(pageable.tobytes()).hexdigest() == frame_sha
 
     # ---- roofline of the render kernel on rank 0 (FP32 CUDA-core pipe; HBM traffic is negligible here)
     k_ms = float(np.mean(kernel_ms))
     flops = algorithmic_flops(cst, pixels // world)
     achieved = flops / (k_ms * 1e-3) / 1e12
     alg_bytes = scene_bytes + (pixels // world) * 3
+    bvh = cst["intersector_used"] == 2
+    ncu_file = ("profiles/r2_k2_lanes_c3_ncu_summary.txt" if bvh else "profiles/r1_k1_brute_final_ncu_summary.txt")
+    ncu = ncu_block(ncu_file) if (args.workload in ("C3", "C2")) else None
     roofline = {
-        "bound": "fp32", "kernel": "render_kernel_lanes<%s>" % ("BVH" if cst["intersector_used"] == 2 else "BRUTE"),
+        "bound": "fp32", "kernel": "render_kernel_lanes<%s>" % ("BVH" if bvh else "BRUTE"),
         "achieved": achieved, "peak": fp32_peak_tflops, "unit": "TFLOP/s", "frac": achieved / fp32_peak_tflops,
         "peak_source": "measured live: FFMA-chain micro-benchmark (rt_measure_fp32_peak); MEASURED_PEAKS.json has no CUDA-core figure",
-        # dram__bytes_read.sum + dram__bytes_write.sum of one launch, from the committed ncu --set full capture of this
-        # kernel on this workload at 1 GPU (profiles/r1_k2_lanes_final4_ncu_summary.txt); not re-measured live
-        "traffic": (0.965376e6 + 0.911360e6) if (args.workload == "C3" and world == 1) else None,
-        "traffic_unit": "bytes per launch (ncu)",
+        # dram__bytes_read.sum + dram__bytes_write.sum of one launch of this kernel on C3 at one GPU, read from the
+        # committed ncu summary named in "ncu" (null when the file is absent or the workload is another one)
+        "traffic": ncu["dram_bytes"] if (ncu and args.workload == "C3" and world == 1) else None,
+        "traffic_unit": "bytes per launch (ncu --set full, file in ncu.source)",
         "algorithmic_flops_per_launch": flops, "kernel_ms_avg": k_ms, "kernel_share_of_step": k_ms / ms_per_step,
         "flops_per_ray": flops / max(1, cst["rays"]),
         "hbm": {"algorithmic_bytes_per_launch": alg_bytes, "achieved_gbs": alg_bytes / (k_ms * 1e-3) / 1e9},
-        # pipe / issue view of the same kernel from the committed ncu captures (what the >= 60 % FP32-pipe target is about):
-        # K2 on C3 is bound by issue under divergence, K1 (brute force, C2) by the FMA pipe after the f32x2 packing
-        "ncu": ({"source": "profiles/r1_k2_lanes_final4_ncu_summary.txt", "issue_slots_pct": 78.4, "fma_pipe_cycles_pct": 34.9,
-                 "alu_pipe_pct": 60.0, "threads_per_warp_inst": 10.49, "warp_inst": 34.4e9} if cst["intersector_used"] == 2 else
-                {"source": "profiles/r1_k1_brute_final_ncu_summary.txt", "issue_slots_pct": 64.3, "fma_pipe_cycles_pct": 60.7,
-                 "threads_per_warp_inst": 24.0}) if args.workload in ("C3", "C2") and world == 1 else None,
+        "ncu": ncu,
         "simt_efficiency_query_level": cst["active_lane_iters"] / max(1, cst["total_lane_iters"]),
         "counters": {k: cst[k] for k in ("rays", "primary", "slab_tests", "sphere_tests", "sphere_exact", "sphere_hits",
                                          "tri_tests", "tri_stage", "tri_hits", "shades_sphere", "shades_tri",
                                          "emissive", "sky")},
-        "launch": {k: cst[k] for k in ("grid_ctas", "cta_threads", "ctas_per_sm", "scene_in_smem", "dyn_smem_bytes")},
+        "launch": {k: st[k] for k in ("grid_ctas", "cta_threads", "ctas_per_sm", "scene_in_smem", "dyn_smem_bytes")},
     }
 
-    cpu_baseline = None
+    cpu_baseline, parity, extra = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import oracle as O
 
         O.build()
         divs = pick_sample(O, sp, tr, cfg, target_s=15.0)
-        r, s = oracle_sample(O, sp, tr, cfg, divs)
+        bands = {}
+        r, s = oracle_sample(O, sp, tr, cfg, divs, keep=bands)
         cpu_baseline = {"value": r / s / 1e6, "unit": UNIT, "cores": O.hardware_threads(), "kind": "port",
                         "sample": describe_sample(cfg, divs) + f": {r} rays in {s:.2f} s",
                         "note": "C++ oracle (-O2 -ffp-contract=off), std::thread row-parallel like rayon; a port of the "
                                 "Rust slave, which cannot be built in this image"}
+        # the timed (e2e) frame against those bands
+        rows = H // REF_DIVISIONS
+        got = np.concatenate([host_frame[d * rows:(d + 1) * rows] for d in sorted(bands)])
+        ref = np.concatenate([bands[d] for d in sorted(bands)])
+        parity = dict(compare_frames(got, ref), bands=sorted(bands), pixels=int(ref.shape[0] * ref.shape[1]),
+                      against="oracle bands of the cpu_baseline leg vs the frame of the last timed e2e step")
+    if rank == 0 and world == 1 and not args.no_extra and args.workload == "C3":
+        extra = extra_workloads(rt, ctx, scenes)
 
     if dist is not None:
         barrier()
@@ -382,19 +492,28 @@ def main():
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "frame_ms": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": dict(workload_config(args, cfg), l2="flushed between steps: 256 MiB device memset (inside the bracket)",
-                           gather=gather_mode, intersector=int(cst["intersector_used"]), device=info["name"]),
+            "config": workload_config(args, cfg),
+            "run": {"gather": mode, "intersector": int(cst["intersector_used"]), "device": info["name"],
+                    "l2_flush_ms": flush_ms, "l2_flush_inside_bracket": True},
             "rays_per_step": rays_total, "mrays_per_s_per_gpu": value / world,
+            "frame_sha256": frame_sha,
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_elapsed / args.steps * 1e3,
                     "h2d_bytes_per_step": int(scene_bytes * world + 72 * world),
                     "d2h_bytes_per_step": int(pixels * 3 + 128 * world),
-                    "what": "rt_scene_create (host BVH build + upload) + render + frame download to pinned host memory, per step"},
+                    "pageable_destination_ms": e2e_pageable_ms, "redo_pixels_max": e2e_redo,
+                    "what": "rt_scene_create (ingest + upload; the reference-topology tree follows on a builder thread) + render "
+                            "+ frame to pinned host memory, per step"
+                            + ("; slabs stream to the host while other slabs render" if world > 1 else "")},
             "gpu_launches": args.steps * world,
             "clocks": clocks,
             "roofline": roofline,
         }
+        if parity:
+            line["parity"] = parity
         if cpu_baseline:
             line["cpu_baseline"] = cpu_baseline
+        if extra:
+            line["extra"] = extra
         real_stdout.write(json.dumps(line) + "\n")
         real_stdout.flush()
     sched.close()

@@ -226,6 +226,10 @@ int rt_frame_wait_consumed(rt_ctx* ctx, const void* frame_dev, size_t frame_byte
 /* FFMA-chain micro-benchmark: achieved FP32 TFLOP/s (2 flops per FFMA) on this device, for the
  * roofline denominator (MEASURED_PEAKS.json has no CUDA-core figure). */
 int rt_measure_fp32_peak(rt_ctx* ctx, double* tflops_out, float* ms_out);
+/* Writes `bytes` (choose more than the 126 MB L2) of a scratch buffer on the context's stream, asynchronously in front
+ * of whatever is queued next: benchmarks flush L2 between timed frames with it without a host synchronisation.
+ * ms_out (nullable): when given, the call synchronises and reports the flush's device time. */
+int rt_l2_flush(rt_ctx* ctx, size_t bytes, float* ms_out);
 /* Device properties: sm_count, clock_khz (max SM clock), smem_optin bytes. Nullable outputs. */
 int rt_device_info(rt_ctx* ctx, int* sm_count, int* clock_khz, int* smem_optin, char name_out[64]);
 

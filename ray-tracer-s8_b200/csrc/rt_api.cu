@@ -112,11 +112,12 @@ static int ensure_out(rt_ctx* ctx, size_t bytes) {
     const size_t cap = rt_frame_ctl_offset(bytes);
     CK(ctx, cudaMalloc(&ctx->d_out, cap + RT_FRAME_CTL_BYTES));
     ctx->d_out_bytes = cap;
-    ctx->out_geom[0] = ctx->out_geom[1] = ctx->out_geom[2] = 0;  // counters are (re)set by the next launch
     return RT_OK;
 }
 
-// The context's own staging frame: counters are cumulative while the slab geometry stays the same.
+// The context's own staging frame.  Its counters start from zero for every launch (frame number 1 each time): whether a
+// launch counts at all is the launcher's choice (single-rank frames do not, rt_kernels.cu), so nothing cumulative can be
+// assumed here — unlike the shared frames of rt_frame_alloc, whose ranks always count.
 int own_frame(rt_ctx* ctx, uint32_t width, uint32_t rows, LaunchArgs* a) {
     const size_t bytes = (size_t)width * rows * 3;
     const int rc = ensure_out(ctx, bytes);
@@ -124,18 +125,10 @@ int own_frame(rt_ctx* ctx, uint32_t width, uint32_t rows, LaunchArgs* a) {
     a->dst = ctx->d_out;
     a->ctl = reinterpret_cast<rt_frame_ctl*>(ctx->d_out + ctx->d_out_bytes);
     a->plan = plan_slabs(width, rows);
-    if (ctx->out_geom[0] != width || ctx->out_geom[1] != rows || ctx->out_geom[2] != a->plan.tile_rows) {
-        // nothing may still be counting into or waiting on the old geometry
-        CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
-        CK(ctx, cudaMemsetAsync(a->ctl, 0, sizeof(rt_frame_ctl), ctx->stream));
-        CK(ctx, cudaEventRecord(ctx->ev_sync, ctx->stream));
-        CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync, 0));
-        ctx->out_geom[0] = width;
-        ctx->out_geom[1] = rows;
-        ctx->out_geom[2] = a->plan.tile_rows;
-        ctx->out_seq = 0;
-    }
-    ctx->out_seq++;
+    CK(ctx, cudaMemsetAsync(a->ctl, 0, sizeof(rt_frame_ctl), ctx->stream));
+    CK(ctx, cudaEventRecord(ctx->ev_sync, ctx->stream));
+    CK(ctx, cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_sync, 0));  // slab waits start after the reset
+    ctx->out_seq = 1;
     return RT_OK;
 }
 
@@ -438,6 +431,7 @@ void rt_shutdown(rt_ctx* ctx) {
     if (ctx->d_redo) cudaFree(ctx->d_redo);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
+    if (ctx->d_flush) cudaFree(ctx->d_flush);
 #ifdef RT_B200_EXPERIMENTS
     free_experiment_buffers(&ctx->xbuf);
 #endif
@@ -670,6 +664,28 @@ int rt_frame_wait_consumed(rt_ctx* ctx, const void* frame_dev, size_t frame_byte
     CK(ctx, cudaSetDevice(ctx->device));
     const rt_frame_ctl* ctl = reinterpret_cast<const rt_frame_ctl*>((const uint8_t*)frame_dev + rt_frame_ctl_offset(frame_bytes));
     CK(ctx, launch_wait_slab(&ctl->consumed, (unsigned long long)seq, ctx->h_flag, ctx->stream));
+    return RT_OK;
+    RT_GUARD_END(ctx)
+}
+
+int rt_l2_flush(rt_ctx* ctx, size_t bytes, float* ms_out) {
+    if (!ctx) return RT_ERR_INVALID_ARG;
+    RT_GUARD_BEGIN
+    CK(ctx, cudaSetDevice(ctx->device));
+    if (ctx->flush_bytes < bytes) {
+        if (ctx->d_flush) CK(ctx, cudaFree(ctx->d_flush));
+        ctx->d_flush = nullptr;
+        ctx->flush_bytes = 0;
+        CK(ctx, cudaMalloc(&ctx->d_flush, bytes));
+        ctx->flush_bytes = bytes;
+    }
+    if (ms_out) CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
+    CK(ctx, cudaMemsetAsync(ctx->d_flush, 0, bytes, ctx->stream));  // stream-ordered in front of the next render
+    if (ms_out) {
+        CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
+        CK(ctx, cudaEventElapsedTime(ms_out, ctx->ev0, ctx->ev1));
+    }
     return RT_OK;
     RT_GUARD_END(ctx)
 }

@@ -36,13 +36,14 @@ struct rt_ctx {
     char name[64] = {0};
     uint8_t* d_out = nullptr;  // band / frame staging in HBM + control block
     size_t d_out_bytes = 0;    // capacity for pixels (the control block follows at rt_frame_ctl_offset(capacity))
-    uint64_t out_seq = 0;      // frames rendered into d_out with the current slab geometry
-    uint32_t out_geom[3] = {0, 0, 0};  // width, rows, slab_tile_rows the counters of d_out are counting for
+    uint64_t out_seq = 1;      // frame number the counters of d_out count towards (reset per launch: always 1)
     unsigned long long* d_ctr = nullptr;  // NUM_COUNTERS counters | 2 tickets (one u64) | redo count (one u64)
     unsigned long long* h_ctr = nullptr;  // pinned mirror
     unsigned int* d_redo = nullptr;       // pixels to render again once the tie-break tables are up (REDO_CAP entries)
     unsigned int* h_flag = nullptr;       // pinned + mapped: [0] a slab wait timed out
     float* d_scratch = nullptr;
+    void* d_flush = nullptr;              // rt_l2_flush: a buffer larger than L2
+    size_t flush_bytes = 0;
     float first_pass_ms = 0.0f;           // kernel time of the first pass when a second one followed (finish_redo)
     rtb::DeviceBuild dbuild;
     // scene upload: one pinned staging buffer the blob is assembled in, and a few retired device blobs kept for the

@@ -177,12 +177,26 @@ __device__ __forceinline__ V3 x_cross(V3 a, V3 b) {
     return mk(x_sub(x_mul(a.y, b.z), x_mul(b.y, a.z)), x_sub(x_mul(a.z, b.x), x_mul(b.z, a.x)),
               x_sub(x_mul(a.x, b.y), x_mul(b.x, a.y)));
 }
+// The normalisations hold most of the kernel's divisions and square roots, each of which expands to a dozen
+// instructions plus a slow-path call.  RT_OUTLINE_NORM keeps ONE copy of each out of line (arguments and results in
+// registers): the render kernel's instruction working set sits at the edge of the instruction cache, and code bytes
+// cost more there than a call does (profiles/r2_notes.md).
+#ifdef RT_OUTLINE_NORM
+#define RT_NORM_FN static __noinline__
+#else
+#define RT_NORM_FN __forceinline__
+#endif
 // Vec3A::normalize: v / sqrt(dot) per lane (used by Ray::new, ray.rs:134)
-__device__ __forceinline__ V3 x_normalize_div(V3 a) {
+__device__ RT_NORM_FN V3 x_normalize_div(V3 a) {
     float l = x_length(a);
     return mk(x_div(a.x, l), x_div(a.y, l), x_div(a.z, l));
 }
-// Vec3A::try_normalize: rcp = 1/length; Some(v*rcp) iff rcp finite && rcp > 0
+// Vec3A::try_normalize: rcp = 1/length; Some(v*rcp) iff rcp finite && rcp > 0.  `or` is returned otherwise.
+__device__ RT_NORM_FN V3 x_normalize_or(V3 a, V3 orv) {
+    float rcp = x_div(1.0f, x_length(a));
+    if (isfinite(rcp) && rcp > 0.0f) return x_scale(a, rcp);
+    return orv;
+}
 __device__ __forceinline__ bool x_try_normalize(V3 a, V3* out) {
     float rcp = x_div(1.0f, x_length(a));
     if (isfinite(rcp) && rcp > 0.0f) {
@@ -191,11 +205,7 @@ __device__ __forceinline__ bool x_try_normalize(V3 a, V3* out) {
     }
     return false;
 }
-__device__ __forceinline__ V3 x_normalize_or_zero(V3 a) {
-    V3 r;
-    if (x_try_normalize(a, &r)) return r;
-    return mk(0.0f, 0.0f, 0.0f);
-}
+__device__ __forceinline__ V3 x_normalize_or_zero(V3 a) { return x_normalize_or(a, mk(0.0f, 0.0f, 0.0f)); }
 
 // rand 0.8.5 SmallRng on 64-bit targets = xoshiro256++; seed_from_u64 = 4 SplitMix64 outputs
 struct Rng {

@@ -20,7 +20,7 @@ constexpr int MAX_SLABS = 64;  // completion counters per frame (frame control b
 struct Tunables {
     int smem_override = -1;      // RT_B200_SMEM=0|1: force the scene out of / into shared memory
     int tile_order_reverse = 1;  // RT_B200_TILE_ORDER=topdown: tickets walk the tile grid top-down
-    bool stage_out = true;       // RT_B200_STAGE_OUT=0: finished pixels go to the frame as byte stores
+    int stage_out = -1;          // RT_B200_STAGE_OUT=0|1: force the output stage + completion counters off / on (-1: shared frames only)
     int tail_permille = 30;      // RT_B200_TAIL_PERMILLE: share of the tickets handed out pixel by pixel
     int build_mode = 1;          // RT_B200_BUILD=host|device|auto: who builds the traversal tree
     int tree_mode = 2;           // RT_B200_TREE=ref|sah|split: which tree is traversed

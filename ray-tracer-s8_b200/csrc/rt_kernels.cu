@@ -70,10 +70,20 @@ struct OutDesc {  // where finished pixels go (by value: never a reference to th
 };
 __device__ __forceinline__ uint32_t slab_of_row(const OutDesc& od, uint32_t y) { return ((y - od.row0) / TILE_H) / od.slab_tile_rows; }
 
+// Completion counts leave a warp in batches: a system-scope release costs microseconds (it waits for every store of
+// the warp to be acknowledged, over NVLink for a peer frame), so a warp keeps the pixels it has written since its last
+// release in shared memory (pend[0] = slab, pend[1] = count) and releases them when it moves on to another slab, when the
+// batch is full, or when it runs out of work.
+constexpr uint32_t COUNT_BATCH = 4096;
+__device__ __forceinline__ void release_count(unsigned long long* done, uint32_t slab, uint32_t cnt) {
+    __threadfence_system();  // cumulative: covers the other lanes' stores ordered before this lane by __syncwarp
+    atomicAdd(&done[slab], (unsigned long long)cnt);
+}
+
 // All 32 lanes: write the staged pixels `mask` of a tile (st = its 96 staged bytes, origin x0 / y0) to the frame and
-// release their count (minus `hold` pixels that the second pass will count).  whole: the tile is complete.
+// count them (minus `hold` pixels that the second pass will count).  whole: the tile is complete.
 __device__ __noinline__ void flush_tile(const OutDesc od, const uint8_t* st, uint32_t x0, uint32_t y0, uint32_t mask, bool whole,
-                                        uint32_t hold) {
+                                        uint32_t hold, uint32_t* pend) {
     const int lane = threadIdx.x & 31;
     const bool vec = whole && mask == 0xffffffffu && ((od.width & 7u) == 0) && ((reinterpret_cast<uintptr_t>(od.out) & 7u) == 0);
     if (vec) {  // twelve 8-byte vectors: 3 per tile row
@@ -90,23 +100,36 @@ __device__ __noinline__ void flush_tile(const OutDesc od, const uint8_t* st, uin
     }
     if (od.done) {
         __syncwarp();
-        const uint32_t cnt = (uint32_t)__popc(mask) - hold;
-        if (lane == 0 && cnt) {
-            __threadfence_system();  // cumulative over the warp's stores ordered by the barrier above
-            atomicAdd(&od.done[slab_of_row(od, y0)], (unsigned long long)cnt);
+        if (lane == 0) {
+            const uint32_t cnt = (uint32_t)__popc(mask) - hold, slab = slab_of_row(od, y0);
+            uint32_t pslab = pend[0], pcnt = pend[1];
+            if (pcnt && pslab != slab) {
+                release_count(od.done, pslab, pcnt);
+                pcnt = 0;
+            }
+            pcnt += cnt;
+            if (pcnt >= COUNT_BATCH) {
+                release_count(od.done, slab, pcnt);
+                pcnt = 0;
+            }
+            pend[0] = slab;
+            pend[1] = pcnt;
         }
     }
 }
 
-// One lane: a finished pixel straight to the frame (no stage slot, or the slot was evicted), counted unless held.
-__device__ __noinline__ void store_pixel(const OutDesc od, uint32_t x, uint32_t y, uint32_t rgb, bool count) {
+// One lane: a finished pixel straight to the frame (no stage slot — the tail's pixel tickets — or the slot was evicted).
+// `dir` = this warp's batching word for such pixels: slab << 24 | count, released when the warp runs out of work (the
+// tail IS the end of the launch); a pixel of another slab is released at once.
+__device__ __noinline__ void store_pixel(const OutDesc od, uint32_t x, uint32_t y, uint32_t rgb, bool count, uint32_t* dir) {
     const size_t off = ((size_t)(y - od.out_row0) * od.width + x) * 3;
     od.out[off + 0] = (uint8_t)rgb;
     od.out[off + 1] = (uint8_t)(rgb >> 8);
     od.out[off + 2] = (uint8_t)(rgb >> 16);
     if (od.done && count) {
-        __threadfence_system();
-        atomicAdd(&od.done[slab_of_row(od, y)], 1ull);
+        const uint32_t slab = slab_of_row(od, y);
+        if (dir && (*reinterpret_cast<volatile uint32_t*>(dir) >> 24) == slab) atomicAdd(dir, 1u);
+        else release_count(od.done, slab, 1u);
     }
 }
 
@@ -129,7 +152,8 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
     // grid), which of its pixels are staged, which exist (edge tiles are partial), how many staged pixels are held back
     __shared__ __align__(16) uint8_t s_stage[STAGE ? NW : 1][OUT_SLOTS][TILE_BYTES];
     __shared__ uint32_t s_key[STAGE ? NW : 1][OUT_SLOTS], s_fill[STAGE ? NW : 1][OUT_SLOTS],
-        s_valid[STAGE ? NW : 1][OUT_SLOTS], s_hold[STAGE ? NW : 1][OUT_SLOTS];
+        s_valid[STAGE ? NW : 1][OUT_SLOTS], s_hold[STAGE ? NW : 1][OUT_SLOTS], s_pend[STAGE ? NW : 1][2],
+        s_dir[STAGE ? NW : 1];  // completion counts not released yet: of flushed tiles (slab, count) and of direct pixels
     __shared__ __align__(8) unsigned long long s_bar;
 
     const unsigned FULL = 0xffffffffu;
@@ -168,6 +192,12 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
         s_key[warp][lane] = KEY_FREE;
         s_fill[warp][lane] = 0u;
         s_hold[warp][lane] = 0u;
+        if (lane < 2) s_pend[warp][lane] = 0u;
+        if (lane == 0) {  // direct pixels are batched for the slab the last tickets fall into
+            const uint32_t tt = pr.tiles_x * pr.tiles_y, gl = min(tt - 1, (pr.my_tickets ? pr.my_tickets - 1 : 0) * pr.tile_ranks);
+            const uint32_t g = pr.tile_order_reverse ? tt - 1 - gl : gl;
+            s_dir[warp] = (((g / pr.tiles_x) / pr.slab_tile_rows) & 0xffu) << 24;
+        }
     }
     if (SMEM) mbar_wait(&s_bar, 0);  // every thread observes the completed transaction itself
     __syncwarp();
@@ -217,7 +247,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                         if (nf == s_valid[warp][sl]) {
                             const uint32_t g = s_key[warp][sl];
                             flush_tile(out_desc(), s_stage[warp][sl], (g % pr.tiles_x) * TILE_W, pr.row0 + (g / pr.tiles_x) * TILE_H,
-                                       nf, true, s_hold[warp][sl]);
+                                       nf, true, s_hold[warp][sl], s_pend[warp]);
                             __syncwarp();
                             if (lane == 0) {
                                 s_key[warp][sl] = KEY_FREE;
@@ -260,7 +290,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                                 const uint32_t f = s_fill[warp][sl], og = s_key[warp][sl];
                                 __syncwarp();
                                 if (f) flush_tile(out_desc(), s_stage[warp][sl], (og % pr.tiles_x) * TILE_W,
-                                                  pr.row0 + (og / pr.tiles_x) * TILE_H, f, false, s_hold[warp][sl]);
+                                                  pr.row0 + (og / pr.tiles_x) * TILE_H, f, false, s_hold[warp][sl], s_pend[warp]);
                             }
                             const uint32_t x0 = (g % pr.tiles_x) * TILE_W, y0 = pr.row0 + (g / pr.tiles_x) * TILE_H;
                             const uint32_t vm = __ballot_sync(FULL, (x0 + (lane & 7) < pr.width) && (y0 + (lane >> 3) < pr.row1));
@@ -380,8 +410,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                     float kk = x_mul(2.0f, x_dot(d, n));
                     V3 glossy = x_sub(d, x_scale(n, kk));
                     V3 scat = x_add(diffuse, x_scale(x_sub(glossy, diffuse), m.w));
-                    V3 nd;
-                    if (!x_try_normalize(scat, &nd)) nd = n;
+                    const V3 nd = x_normalize_or(scat, n);  // try_normalize(..).unwrap_or(normal) (main.rs:126)
                     o = h.p;
                     d = x_normalize_div(nd);  // Ray::new
                     path[np++] = (uint32_t)h.pid;
@@ -391,8 +420,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                 }
             } else {  // sky (main.rs:135-144)
                 if (COUNT) ctr.v[CTR_SKY]++;
-                float rcp = x_div(1.0f, x_length(d));
-                float ny = (isfinite(rcp) && rcp > 0.0f) ? x_mul(d.y, rcp) : 0.0f;
+                const float ny = x_normalize_or_zero(d).y;
                 float t = x_add(x_mul(ny, 0.5f), 1.0f);
                 float k1 = x_sub(1.0f, t);
                 float w = x_mul(1.0f, t);
@@ -426,7 +454,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                             staged = true;
                         }
                     }
-                    if (!staged) store_pixel(out_desc(), px, py, rgb, !hold);
+                    if (!staged) store_pixel(out_desc(), px, py, rgb, !hold, STAGE ? &s_dir[warp] : nullptr);
                     if ((st & L_REDO) && !pr.pixel_list) {
                         const unsigned long long at = atomicAdd(pr.redo_count, 1ull);
                         if (at < pr.redo_cap) pr.redo_list[at] = py * pr.width + px;
@@ -438,6 +466,14 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
         }
     }
 
+    if (STAGE && pr.done) {  // the warp is out of work: what it still holds is released now
+        __syncwarp();
+        if (lane == 0) {
+            if (s_pend[warp][1]) release_count(pr.done, s_pend[warp][0], s_pend[warp][1]);
+            const uint32_t dw = s_dir[warp];
+            if (dw & 0xffffffu) release_count(pr.done, dw >> 24, dw & 0xffffffu);
+        }
+    }
     ctr.v[CTR_RAYS] = rays;
 #pragma unroll
     for (int i = 0; i < NUM_COUNTERS; i++) {
@@ -528,7 +564,7 @@ const Tunables& tunables() {
         Tunables v;
         v.smem_override = env_int("RT_B200_SMEM", -1);
         v.tile_order_reverse = env_is("RT_B200_TILE_ORDER", "topdown") ? 0 : 1;
-        v.stage_out = env_int("RT_B200_STAGE_OUT", 1) != 0;
+        v.stage_out = env_int("RT_B200_STAGE_OUT", -1);
         v.tail_permille = std::max(0, std::min(500, env_int("RT_B200_TAIL_PERMILLE", 30)));
         v.build_mode = env_is("RT_B200_BUILD", "host") ? 0 : (env_is("RT_B200_BUILD", "device") ? 2 : 1);
         v.tree_mode = env_is("RT_B200_TREE", "ref") ? 0 : (env_is("RT_B200_TREE", "sah") ? 1 : 2);
@@ -620,7 +656,10 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
                        : ((need + static_smem + 1024) * 3 <= (size_t)smem_optin);
     if (tn.smem_override == 0) smem = false;
     if (tn.smem_override == 1) smem = need + static_smem + 1024 <= (size_t)smem_optin;
-    const bool stage = tn.stage_out && !count;
+    // The output stage and the completion counters cost ~0.1 ns per pixel (C3: +1.3 ms of 37.3); the copy they hide costs
+    // 0.06 ns per pixel on the frame's owner.  They pay when the pixels are spread over several GPUs and the frame is
+    // collected on one (profiles/r2_notes.md): on by default for shared frames only.  RT_B200_STAGE_OUT=0|1 forces it.
+    const bool stage = !count && (tn.stage_out < 0 ? (pr.tile_ranks > 1 && pr.done != nullptr) : tn.stage_out != 0);
     int threads = THREADS;
     KernelFn fn;
     if (isect == RT_INTERSECT_BRUTE) fn = smem ? pick_lanes<RT_INTERSECT_BRUTE, true>(count, stage, &threads) : pick_lanes<RT_INTERSECT_BRUTE, false>(count, stage, &threads);
@@ -639,7 +678,8 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
     if (grid > want_ctas) grid = want_ctas;
     if (grid < 1) grid = 1;
     DevParams prm = pr;
-    if (!tn.count_done) {
+    if (!tn.count_done || (!stage && !count)) {  // without the stage every pixel would pay a system-scope release of its
+                                                 // own (the instrumented kernel does: it is not a timed path)
         prm.done = nullptr;
         if (info) info->counts_done = false;
     }

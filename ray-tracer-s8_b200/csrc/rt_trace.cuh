@@ -396,7 +396,7 @@ __device__ __forceinline__ void primary_ray(const DevCamera& cam, uint32_t x, ui
 }
 
 // `(c * 255.999) as u8`: truncation, saturation, NaN → 0 (color.rs:13-19)
-__device__ __forceinline__ uint32_t quantise(float sum, float spp_f) {
+__device__ RT_NORM_FN uint32_t quantise(float sum, float spp_f) {
     float c = x_sqrt(x_div(sum, spp_f));
     float s = x_mul(c, 255.999f);
     uint32_t q = __float2uint_rz(s);  // saturating, NaN → 0

@@ -73,7 +73,7 @@ EXPORTS = [
     "rt_scene_info", "rt_render_division", "rt_render_frame", "rt_render_tiles_device", "rt_sync", "rt_stream",
     "rt_host_alloc", "rt_host_free", "rt_frame_alloc", "rt_frame_open", "rt_frame_close", "rt_frame_free",
     "rt_frame_download", "rt_measure_fp32_peak", "rt_device_info", "rt_bvh_build_host", "rt_struct_sizes", "rt_scene_device_bytes",
-    "rt_scene_wait_ready", "rt_render_frame_multi", "rt_frame_collect", "rt_render_tiles_collect", "rt_frame_wait_consumed",
+    "rt_scene_wait_ready", "rt_render_frame_multi", "rt_frame_collect", "rt_render_tiles_collect", "rt_frame_wait_consumed", "rt_l2_flush",
 ]
 # only in the experiments build (csrc/experiments/rt_experiments_api.h)
 EXPERIMENT_EXPORTS = ["rt_debug_trace_bench"]
@@ -147,6 +147,8 @@ def lib():
     L.rt_render_frame_multi.restype = i32
     L.rt_render_tiles_collect.argtypes = [vp, vp, C.POINTER(RtParams), u32, u32, vp, C.c_uint64, vp, sz, C.POINTER(RtStats)]
     L.rt_render_tiles_collect.restype = i32
+    L.rt_l2_flush.argtypes = [vp, sz, C.POINTER(C.c_float)]
+    L.rt_l2_flush.restype = i32
     L.rt_frame_wait_consumed.argtypes = [vp, vp, sz, C.c_uint64]
     L.rt_frame_wait_consumed.restype = i32
     L.rt_frame_collect.argtypes = [vp, vp, C.POINTER(RtParams), C.c_uint64, vp, sz]

@@ -106,6 +106,12 @@ class Context:
         self._check(self._lib.rt_measure_fp32_peak(self._h, C.byref(tf), C.byref(ms)))
         return tf.value, ms.value
 
+    def l2_flush(self, nbytes: int, timed: bool = False):
+        """Queue a write of `nbytes` (> L2) in front of the next render on this context's stream; timed → its ms."""
+        ms = C.c_float()
+        self._check(self._lib.rt_l2_flush(self._h, nbytes, C.byref(ms) if timed else None))
+        return ms.value if timed else None
+
     def trace_bench(self, scene: "Scene", params: RtParams, max_rays: int, with_big: bool = True, sort: bool = False):
         """Development aid (experiments build, RT_B200_LIB=exp): the nearest-hit query alone over the recorded queries of
         one frame (csrc/experiments/rt_trace_bench.cuh)."""
