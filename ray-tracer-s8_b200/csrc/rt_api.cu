@@ -154,8 +154,7 @@ int launch(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, const LaunchAr
     pr.redo_cap = RT_REDO_CAP;
     pr.pixel_list = a.pixel_list;
     pr.list_count = a.list_count;
-    pr.done = (a.ctl && (!a.pixel_list || a.defer_redo)) ? a.ctl->done : nullptr;
-    pr.defer_redo = (a.defer_redo && !a.pixel_list) ? 1 : 0;
+    pr.done = a.ctl ? a.ctl->done : nullptr;
     pr.redo_slab = ctx->d_ctr + RT_CTR_REDO_SLAB;
     pr.slab_tile_rows = a.plan.tile_rows ? a.plan.tile_rows : 1;
 #ifdef RT_B200_EXPERIMENTS
@@ -168,9 +167,9 @@ int launch(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, const LaunchAr
         if (src) return src;
     }
 #endif
-    DevScene dev = scene_view(scene);
-    if (a.force_noaux) dev.aux_ready = 0;
+    const DevScene dev = scene_view(scene);
     CK(ctx, cudaMemsetAsync(ctx->d_ctr, 0, RT_CTR_SLOTS * sizeof(unsigned long long), ctx->stream));
+    if (!a.pixel_list) CK(ctx, cudaMemsetAsync(ctx->d_redo, 0, RT_REDO_CAP * sizeof(unsigned int), ctx->stream));
     CK(ctx, cudaEventRecord(ctx->ev0, ctx->stream));
     CK(ctx, launch_render(dev, r.cam, pr, r.isect, r.p.collect_counters != 0, ctx->sm_count, ctx->smem_optin, ctx->stream, info));
     CK(ctx, cudaEventRecord(ctx->ev1, ctx->stream));
@@ -192,54 +191,42 @@ int finish_redo(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, const Lau
     *redone = 0;
     int rc = read_counters(ctx);
     if (rc) return rc;
-    const unsigned long long want = ctx->h_ctr[RT_CTR_REDO];
+    const unsigned long long count = ctx->h_ctr[RT_CTR_REDO];
+    const unsigned long long taken = ctx->h_ctr[RT_CTR_TICKET2] & 0xffffffffull;  // second passes done inside the kernel
     ctx->first_pass_ms = 0.0f;
-    if (want == 0) return RT_OK;
-    cudaEventElapsedTime(&ctx->first_pass_ms, ctx->ev0, ctx->ev1);  // the later passes re-record the events
+    if (count == 0) return RT_OK;
+    *redone = count > RT_REDO_CAP ? 0xffffffffu : (uint32_t)count;
+    if (count <= RT_REDO_CAP && taken >= count) return RT_OK;
+    cudaEventElapsedTime(&ctx->first_pass_ms, ctx->ev0, ctx->ev1);  // the second pass re-records the events
+    unsigned long long first[NUM_COUNTERS], slab_counts[MAX_SLABS];
+    memcpy(first, ctx->h_ctr, sizeof first);
+    memcpy(slab_counts, ctx->h_ctr + RT_CTR_REDO_SLAB, sizeof slab_counts);
     rc = scene_settle(ctx, scene);  // the tables must be there now
     if (rc) return rc;
     LaunchInfo li;
-    if (want > RT_REDO_CAP) {
-        // more than the list holds: the whole launch again (frame counters untouched: ctl off); its counters are final
-        unsigned long long slab_counts[MAX_SLABS];
-        memcpy(slab_counts, ctx->h_ctr + RT_CTR_REDO_SLAB, sizeof slab_counts);
-        LaunchArgs b = a;
+    LaunchArgs b = a;
+    if (count > RT_REDO_CAP) {
+        // more than the list holds: the whole launch again, without counting (every pixel it had not held back is
+        // counted already); the pixels still held back are then counted slab by slab from the first pass's numbers
         b.ctl = nullptr;
         rc = launch(ctx, scene, r, b, &li);
         if (rc) return rc;
-        *redone = 0xffffffffu;
-        if (a.defer_redo && a.ctl) {  // the deferred pixels are counted now, slab by slab (the first pass kept their numbers)
+        if (a.ctl) {
             memcpy(ctx->h_ctr + RT_CTR_REDO_SLAB, slab_counts, sizeof slab_counts);
             CK(ctx, cudaMemcpyAsync(ctx->d_ctr + RT_CTR_REDO_SLAB, ctx->h_ctr + RT_CTR_REDO_SLAB, sizeof slab_counts,
                                     cudaMemcpyHostToDevice, ctx->stream));
             CK(ctx, launch_add_counts(a.ctl->done, ctx->d_ctr + RT_CTR_REDO_SLAB, MAX_SLABS, ctx->stream));
         }
-        return read_counters(ctx);
+        return read_counters(ctx);  // the counters of the repeated launch are the frame's
     }
-    // The listed pixels again.  Counters of the final image = first pass - (the listed pixels as the first pass saw
-    // them: traced once more without the tables, into nothing but the counters) + (the listed pixels with the tables).
-    unsigned long long first[NUM_COUNTERS], minus[NUM_COUNTERS];
-    memcpy(first, ctx->h_ctr, sizeof first);
-    LaunchArgs b = a;
-    b.pixel_list = ctx->d_redo;
-    b.list_count = (uint32_t)want;
-    b.force_noaux = true;
-    b.ctl = nullptr;
+    // the listed pixels nobody got to inside the kernel, with the tables: counted now (their first pass held them back)
+    b.pixel_list = ctx->d_redo + taken;
+    b.list_count = (uint32_t)(count - taken);
     rc = launch(ctx, scene, r, b, &li);
     if (rc) return rc;
     rc = read_counters(ctx);
     if (rc) return rc;
-    memcpy(minus, ctx->h_ctr, sizeof minus);
-    b.force_noaux = false;
-    b.ctl = a.ctl;
-    rc = launch(ctx, scene, r, b, &li);
-    if (rc) return rc;
-    rc = read_counters(ctx);
-    if (rc) return rc;
-    for (int i = 0; i < NUM_COUNTERS; i++) ctx->h_ctr[i] = first[i] - minus[i] + ctx->h_ctr[i];
-    float ms = 0.0f;
-    cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1);
-    *redone = (uint32_t)want;
+    for (int i = 0; i < NUM_COUNTERS; i++) ctx->h_ctr[i] += first[i];  // queries of both passes (stats.redo_pixels says so)
     return RT_OK;
 }
 
@@ -281,8 +268,35 @@ int finish_stats(rt_ctx* ctx, const Resolved& r, uint64_t pixels, rt_stats* st,
     return RT_OK;
 }
 
-int collect_slabs(rt_ctx* ctx, const uint8_t* frame_dev, const rt_frame_ctl* ctl, const SlabPlan& plan, uint64_t seq,
-                  uint8_t* out_rgb, bool reverse_order) {
+int enqueue_slab_copies(rt_ctx* ctx, const uint8_t* frame_dev, const rt_frame_ctl* ctl, const SlabPlan& plan, uint64_t seq,
+                        uint8_t* out_rgb, bool reverse_order, SlabJob* job) {
+    job->plan = plan;
+    job->out = out_rgb;
+    job->pinned = out_rgb;
+    job->reverse = reverse_order;
+    const size_t bytes = (size_t)plan.rows * plan.width * 3;
+    if (out_rgb) {
+        cudaPointerAttributes attr;
+        const cudaError_t pe = cudaPointerGetAttributes(&attr, out_rgb);
+        (void)cudaGetLastError();
+        if (pe != cudaSuccess || attr.type == cudaMemoryTypeUnregistered) {
+            // pageable destination: an asynchronous copy would block this thread until the slab is complete; go through
+            // pinned staging and copy slab by slab on the host as they land
+            if (ctx->h_frame_bytes < bytes) {
+                if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
+                ctx->h_frame = nullptr;
+                ctx->h_frame_bytes = 0;
+                CK(ctx, cudaMallocHost(&ctx->h_frame, bytes));
+                ctx->h_frame_bytes = bytes;
+            }
+            job->pinned = ctx->h_frame;
+            while (ctx->slab_events.size() < plan.slabs) {
+                cudaEvent_t e;
+                CK(ctx, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                ctx->slab_events.push_back(e);
+            }
+        }
+    }
     ctx->h_flag[0] = 0;
     for (uint32_t i = 0; i < plan.slabs; i++) {
         // tickets walk the frame bottom-up by default: the last slab completes first
@@ -291,12 +305,26 @@ int collect_slabs(rt_ctx* ctx, const uint8_t* frame_dev, const rt_frame_ctl* ctl
         CK(ctx, launch_wait_slab(&ctl->done[s], target, ctx->h_flag, ctx->copy_stream));
         if (out_rgb) {
             const size_t off = (size_t)plan.first_row(s) * plan.width * 3;
-            const size_t bytes = (size_t)plan.row_count(s) * plan.width * 3;
-            CK(ctx, cudaMemcpyAsync(out_rgb + off, frame_dev + off, bytes, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            const size_t nb = (size_t)plan.row_count(s) * plan.width * 3;
+            CK(ctx, cudaMemcpyAsync(job->pinned + off, frame_dev + off, nb, cudaMemcpyDeviceToHost, ctx->copy_stream));
+            if (job->pinned != out_rgb) CK(ctx, cudaEventRecord(ctx->slab_events[s], ctx->copy_stream));
         }
     }
     // the frame is out of the buffer: ranks waiting to overwrite it may go on (rt_frame_wait_consumed)
     CK(ctx, launch_set_u64(const_cast<unsigned long long*>(&ctl->consumed), (unsigned long long)seq, ctx->copy_stream));
+    return RT_OK;
+}
+
+int finish_slab_copies(rt_ctx* ctx, const SlabJob& job) {
+    if (job.out && job.pinned != job.out) {
+        for (uint32_t i = 0; i < job.plan.slabs; i++) {
+            const uint32_t s = job.reverse ? job.plan.slabs - 1 - i : i;
+            CK(ctx, cudaEventSynchronize(ctx->slab_events[s]));
+            if (ctx->h_flag[0]) break;
+            const size_t off = (size_t)job.plan.first_row(s) * job.plan.width * 3;
+            memcpy(job.out + off, job.pinned + off, (size_t)job.plan.row_count(s) * job.plan.width * 3);
+        }
+    }
     CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
     if (ctx->h_flag[0]) return set_err(ctx, RT_ERR_TIMEOUT, "a slab of the frame did not complete within 20 s");
     return RT_OK;
@@ -315,14 +343,18 @@ int render_and_collect(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, co
     int rc = launch(ctx, scene, r, a, &li);
     if (rc) return rc;
     const bool streamed = li.counts_done && a.ctl && (a.plan.slabs > 1 || a.tile_ranks > 1);
+    SlabJob job;
     if (streamed) {
-        rc = collect_slabs(ctx, frame_dev, a.ctl, a.plan, seq, out_rgb, tunables().tile_order_reverse != 0);
+        rc = enqueue_slab_copies(ctx, frame_dev, a.ctl, a.plan, seq, out_rgb, tunables().tile_order_reverse != 0, &job);
         if (rc) return rc;
     }
     uint32_t redone = 0;
-    rc = finish_redo(ctx, scene, r, a, &redone);  // synchronises the render stream
+    rc = finish_redo(ctx, scene, r, a, &redone);  // own kernel done; pixels it still held back are final (and counted) now
     if (rc) return rc;
-    if (!streamed || redone) {
+    if (streamed) {
+        rc = finish_slab_copies(ctx, job);
+        if (rc) return rc;
+    } else {
         CK(ctx, cudaMemcpyAsync(out_rgb, frame_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -430,6 +462,8 @@ void rt_shutdown(rt_ctx* ctx) {
     if (ctx->h_ctr) cudaFreeHost(ctx->h_ctr);
     if (ctx->d_redo) cudaFree(ctx->d_redo);
     if (ctx->h_flag) cudaFreeHost(ctx->h_flag);
+    if (ctx->h_frame) cudaFreeHost(ctx->h_frame);
+    for (cudaEvent_t e : ctx->slab_events) cudaEventDestroy(e);
     if (ctx->d_scratch) cudaFree(ctx->d_scratch);
     if (ctx->d_flush) cudaFree(ctx->d_flush);
 #ifdef RT_B200_EXPERIMENTS
@@ -520,7 +554,6 @@ int rt_render_tiles_device(rt_ctx* ctx, const rt_scene* scene, const rt_params* 
     a.tile_ranks = tile_ranks;
     a.dst = (uint8_t*)frame_dev;
     a.out_row0 = 0;
-    a.defer_redo = true;  // the frame's owner may copy a slab the moment its count is complete
     a.plan = plan_slabs(r.p.width, r.p.height);
     a.ctl = reinterpret_cast<rt_frame_ctl*>((uint8_t*)frame_dev + rt_frame_ctl_offset((size_t)r.p.width * r.p.height * 3));
     LaunchInfo li;
@@ -653,7 +686,10 @@ int rt_frame_collect(rt_ctx* ctx, const void* frame_dev, const rt_params* params
     CK(ctx, cudaSetDevice(ctx->device));
     const SlabPlan plan = plan_slabs(params->width, params->height);
     const rt_frame_ctl* ctl = reinterpret_cast<const rt_frame_ctl*>((const uint8_t*)frame_dev + rt_frame_ctl_offset(bytes));
-    return collect_slabs(ctx, (const uint8_t*)frame_dev, ctl, plan, seq, out_rgb, tunables().tile_order_reverse != 0);
+    SlabJob job;
+    const int rc = enqueue_slab_copies(ctx, (const uint8_t*)frame_dev, ctl, plan, seq, out_rgb, tunables().tile_order_reverse != 0, &job);
+    if (rc) return rc;
+    return finish_slab_copies(ctx, job);
     RT_GUARD_END(ctx)
 }
 

@@ -41,6 +41,9 @@ struct rt_ctx {
     unsigned long long* h_ctr = nullptr;  // pinned mirror
     unsigned int* d_redo = nullptr;       // pixels to render again once the tie-break tables are up (REDO_CAP entries)
     unsigned int* h_flag = nullptr;       // pinned + mapped: [0] a slab wait timed out
+    uint8_t* h_frame = nullptr;           // pinned staging for frames streamed to a pageable destination
+    size_t h_frame_bytes = 0;
+    std::vector<cudaEvent_t> slab_events; // one per slab, for the pageable path's per-slab host copies
     float* d_scratch = nullptr;
     void* d_flush = nullptr;              // rt_l2_flush: a buffer larger than L2
     size_t flush_bytes = 0;
@@ -62,10 +65,11 @@ struct rt_ctx {
 #endif
 };
 constexpr uint32_t RT_REDO_CAP = 1u << 16;
-constexpr int RT_CTR_TICKETS = rtb::NUM_COUNTERS;      // slot of the two 32-bit tickets
-constexpr int RT_CTR_REDO = rtb::NUM_COUNTERS + 1;     // slot of the redo count
-constexpr int RT_CTR_REDO_SLAB = rtb::NUM_COUNTERS + 2;  // MAX_SLABS per-slab counts of deferred pixels
-constexpr int RT_CTR_SLOTS = rtb::NUM_COUNTERS + 2 + rtb::MAX_SLABS;
+constexpr int RT_CTR_TICKETS = rtb::NUM_COUNTERS;      // two 32-bit tickets: whole tiles | the tail's pixels
+constexpr int RT_CTR_TICKET2 = rtb::NUM_COUNTERS + 1;  // 32-bit ticket: redo-list entries taken inside the kernel (| pad)
+constexpr int RT_CTR_REDO = rtb::NUM_COUNTERS + 2;     // pixels appended to the redo list
+constexpr int RT_CTR_REDO_SLAB = rtb::NUM_COUNTERS + 3;  // MAX_SLABS per-slab counts of pixels still held back
+constexpr int RT_CTR_SLOTS = rtb::NUM_COUNTERS + 3 + rtb::MAX_SLABS;
 
 // The reference-topology tree (bvh_impl.rs:229-364) is needed only to break exact-distance ties (its DFS leaf order,
 // shapes/mod.rs:177-182) and for rays with a zero direction component (ancestor boxes, ray.rs:174-194).  It is built
@@ -127,10 +131,6 @@ struct LaunchArgs {
     SlabPlan plan;
     const unsigned int* pixel_list = nullptr;  // redo launch: render exactly these pixels (y * width + x)
     uint32_t list_count = 0;
-    // the frame belongs to another rank that may copy a slab out the moment its count is complete: pixels that need a
-    // second pass are counted by that pass, not before
-    bool defer_redo = false;
-    bool force_noaux = false;  // second-pass accounting: trace as if the tie-break tables had not landed (counters only)
 };
 // The context's own staging frame (+ control block) for a launch of `rows` rows: fills dst / ctl / plan, bumps out_seq.
 int own_frame(rt_ctx* ctx, uint32_t width, uint32_t rows, LaunchArgs* a);
@@ -141,10 +141,19 @@ int launch(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, const LaunchAr
 int finish_redo(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, const LaunchArgs& a, uint32_t* redone);
 int finish_stats(rt_ctx* ctx, const Resolved& r, uint64_t pixels, rt_stats* st,
                  std::chrono::steady_clock::time_point t0, const LaunchInfo& li);
-// On the frame owner: for every slab wait (on the device, copy stream) until frame number `seq` of it is complete and
-// copy it to out_rgb as it lands; out_rgb == nullptr only waits.  Returns when all slabs are done.
-int collect_slabs(rt_ctx* ctx, const uint8_t* frame_dev, const rt_frame_ctl* ctl, const SlabPlan& plan, uint64_t seq,
-                  uint8_t* out_rgb, bool reverse_order);
+// On the frame owner.  enqueue: for every slab, on the copy stream, wait (on the device) until frame number `seq` of it
+// is complete, then copy it towards out_rgb (nullptr: only wait) — asynchronous; a pageable out_rgb is reached through a
+// pinned staging frame.  finish: host side of the same — returns when every slab is in out_rgb.  Between the two the
+// caller is free to finish its own kernel (second pass included): nothing here blocks the render stream.
+struct SlabJob {
+    SlabPlan plan;
+    uint8_t* out = nullptr;       // caller's destination
+    uint8_t* pinned = nullptr;    // where the device copies go (== out when out is pinned)
+    bool reverse = false;
+};
+int enqueue_slab_copies(rt_ctx* ctx, const uint8_t* frame_dev, const rt_frame_ctl* ctl, const SlabPlan& plan, uint64_t seq,
+                        uint8_t* out_rgb, bool reverse_order, SlabJob* job);
+int finish_slab_copies(rt_ctx* ctx, const SlabJob& job);
 
 }  // namespace rtb
 

@@ -54,8 +54,10 @@ struct DevScene {
     // ref_box[2*(2*node + side)] = that child's box (min | max), unpadded
     const uint32_t* ref_up;
     const float4* ref_box;
-    int aux_ready;         // rank / ref_up / ref_box have landed (they are built beside the upload, rt_scene.cu); while 0,
-                           // a query that needs them marks its pixel for a second pass instead
+    int aux_ready;         // rank / ref_up / ref_box had landed when the kernel was launched (they are built beside the upload,
+                           // rt_scene.cu).  While 0, a query that needs them polls *aux_flag (set once they land) and, if
+                           // still 0, marks its pixel for a second pass
+    const int* aux_flag;
     uint32_t ns, nt, ni;   // ni = inner nodes of the reference tree
 #ifdef RT_B200_EXPERIMENTS
     uint32_t big_pid[MAX_BIG];  // the big primitives' ids, as the A/B kernels read them
@@ -71,6 +73,7 @@ struct DevScene {
 #endif
 };
 constexpr uint32_t UP_ROOT = 0xffffffffu;
+constexpr uint32_t REDO_VALID = 0x80000000u;
 
 struct DevCamera {            // Camera::new (camera.rs:19-47), evaluated on the host in reference order
     float org[3], llc[3], hor[3], ver[3];
@@ -98,15 +101,14 @@ struct DevParams {
     unsigned long long* done;
     uint32_t slab_tile_rows;
     unsigned long long* counters;  // NUM_COUNTERS
-    // second pass (rt_api.cu finish_redo): pixels whose queries needed the tie-break tables before they had landed are
-    // appended to redo_list (y * width + x; *redo_count may exceed the capacity: then the whole launch is repeated);
-    // a launch with pixel_list != nullptr renders exactly those pixels, from pixel tickets only
+    // second pass: a pixel whose queries needed the tie-break tables before they had landed is appended to redo_list
+    // (REDO_VALID | (y * width + x); the list is zeroed before the launch) and NOT added to `done`; redo_slab[slab] counts
+    // such pixels.  When the launch runs out of tickets and the tables have landed meanwhile, idle lanes render listed
+    // pixels again (ticket[2] = entries taken) — what is left (or everything, if *redo_count exceeds the capacity) is the
+    // host's (rt_api.cu finish_redo), as a launch with pixel_list != nullptr: exactly those pixels, pixel tickets only
     unsigned int* redo_list;
     unsigned long long* redo_count;
     uint32_t redo_cap;
-    // defer_redo != 0 (a non-owner rank of a shared frame): such a pixel is NOT added to `done` now but by the second
-    // pass, so a slab the frame owner sees complete is final; redo_slab[slab] counts them (for the case the list overflows)
-    int defer_redo;
     unsigned long long* redo_slab;
     const unsigned int* pixel_list;
     uint32_t list_count;

@@ -142,6 +142,7 @@ constexpr uint32_t L_FINISHED = 2u;       constexpr uint32_t W_IN_TAIL = 2u;
 constexpr uint32_t L_PEND = 4u;           constexpr int W_SLOT_SHIFT = 4;    // 3 bits: slot + 1 of the warp's current tile
 constexpr uint32_t L_REDO = 8u;           constexpr int W_NEXT_SHIFT = 8;    // 6 bits: next pixel of the current tile
 constexpr int L_SLOT_SHIFT = 4;           // 3 bits: output-stage slot + 1 of this lane's pixel (0: straight to the frame)
+constexpr uint32_t L_SECOND = 128u;       // this pixel comes from the redo list: its first pass was held back, not counted
 
 template <int ISECT, bool SMEM, bool COUNT, bool STAGE, int MINB, int TPB>
 __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene sc, const DevCamera cam,
@@ -307,7 +308,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                     }
                 }
                 // (2) per wanting lane: a candidate pixel (x == width: none)
-                uint32_t x = pr.width, y = 0, slot1 = 0;
+                uint32_t x = pr.width, y = 0, slot1 = 0, second = 0;
                 const uint32_t my = __popc(want & lt_mask);
                 const bool wants = (st & (L_HAVE | L_FINISHED)) == 0;
                 if (ws & W_IN_TAIL) {
@@ -316,14 +317,46 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                     if (lane == 0) base = atomicAdd(&pr.tile_counter[1], (unsigned int)__popc(want));
                     base = __shfl_sync(FULL, base, 0);
                     if (base >= tail_pixels) {
-                        ws &= ~(W_TILES_LEFT | W_IN_TAIL);
-                        if (!(st & L_HAVE)) st |= L_FINISHED;
-                        break;
+                        // The tickets are gone.  Pixels that waited for the tie-break tables are rendered again by
+                        // whoever is idle, once the tables have landed: lane 0 takes up to one entry per wanting lane.
+                        uint32_t t0 = 0, n_take = 0;
+                        if (!pr.pixel_list && lane == 0) {
+                            int landed = sc.aux_ready;
+                            if (!landed) asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(landed) : "l"(sc.aux_flag) : "memory");
+                            const unsigned long long cnt = *reinterpret_cast<volatile unsigned long long*>(pr.redo_count);
+                            if (landed && cnt <= pr.redo_cap) {  // more than the list holds: the host repeats the launch
+                                for (;;) {
+                                    t0 = *reinterpret_cast<volatile unsigned int*>(&pr.tile_counter[2]);
+                                    n_take = min((uint32_t)__popc(want), (uint32_t)cnt - min((uint32_t)cnt, t0));
+                                    if (n_take == 0 || atomicCAS(&pr.tile_counter[2], t0, t0 + n_take) == t0) break;
+                                }
+                            }
+                        }
+                        t0 = __shfl_sync(FULL, t0, 0);
+                        n_take = __shfl_sync(FULL, n_take, 0);
+                        if (n_take == 0) {
+                            ws &= ~(W_TILES_LEFT | W_IN_TAIL);
+                            if (!(st & L_HAVE)) st |= L_FINISHED;
+                            break;
+                        }
+                        if (wants && my < n_take) {
+                            uint32_t e;  // the entry is written right after its index was reserved: wait for it
+                            for (uint32_t spin = 0;; spin++) {
+                                e = *reinterpret_cast<volatile unsigned int*>(&pr.redo_list[t0 + my]);
+                                if (e & REDO_VALID) break;
+                                if (spin > (1u << 24)) __trap();
+                            }
+                            e &= ~REDO_VALID;
+                            x = e % pr.width;
+                            y = e / pr.width;
+                            second = L_SECOND;
+                        }
+                        base = tail_pixels;  // no ticket of the tail for anybody in this round
                     }
                     const uint32_t idx = base + my;
                     if (wants && idx < tail_pixels) {
-                        if (pr.pixel_list) {  // second pass: exactly the listed pixels
-                            const uint32_t p = pr.pixel_list[idx];
+                        if (pr.pixel_list) {  // the host's second pass: exactly the listed pixels
+                            const uint32_t p = pr.pixel_list[idx] & ~REDO_VALID;
                             x = p % pr.width;
                             y = p / pr.width;
                         } else {
@@ -348,7 +381,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                 // (3) the lane takes its pixel (tiles on the right / bottom edge are partial)
                 if (x < pr.width && y < pr.row1) {
                     px = x; py = y;
-                    st = L_HAVE | (slot1 << L_SLOT_SHIFT);
+                    st = L_HAVE | (slot1 << L_SLOT_SHIFT) | second;
                     rng.seed_from_u64(pr.seed + ((uint64_t)y * pr.width + x));
                     sr = sg = sb = 0.0f;
                     s = 0;
@@ -441,8 +474,8 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                 left = 0;
                 if (s == pr.spp) {  // pixel finished (main.rs:78-81)
                     const uint32_t rgb = quantise(sr, spp_f) | (quantise(sg, spp_f) << 8) | (quantise(sb, spp_f) << 16);
-                    // a pixel that goes to the second pass of a rank that does not own the frame is counted there
-                    const bool hold = (st & L_REDO) && pr.defer_redo;
+                    // a pixel that goes to the second pass is counted there: a slab whose count is complete is final
+                    const bool hold = (st & L_REDO) != 0;
                     const int my_sl = (int)((st >> L_SLOT_SHIFT) & 7u) - 1;
                     bool staged = false;
                     if (STAGE && my_sl >= 0) {
@@ -455,12 +488,14 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                         }
                     }
                     if (!staged) store_pixel(out_desc(), px, py, rgb, !hold, STAGE ? &s_dir[warp] : nullptr);
-                    if ((st & L_REDO) && !pr.pixel_list) {
+                    if (st & L_REDO) {  // (a second pass never gets here: the tables are there for it)
+                        atomicAdd(&pr.redo_slab[((py - pr.row0) / TILE_H) / pr.slab_tile_rows], 1ull);
                         const unsigned long long at = atomicAdd(pr.redo_count, 1ull);
-                        if (at < pr.redo_cap) pr.redo_list[at] = py * pr.width + px;
-                        if (pr.defer_redo) atomicAdd(&pr.redo_slab[((py - pr.row0) / TILE_H) / pr.slab_tile_rows], 1ull);
+                        if (at < pr.redo_cap) pr.redo_list[at] = REDO_VALID | (py * pr.width + px);
+                    } else if (st & L_SECOND) {
+                        atomicAdd(&pr.redo_slab[((py - pr.row0) / TILE_H) / pr.slab_tile_rows], ~0ull);  // no longer held back
                     }
-                    st = (st & ~(L_HAVE | L_REDO | L_PEND)) | (staged ? L_PEND : 0u);  // the slot bits stay for the collect
+                    st = (st & ~(L_HAVE | L_REDO | L_SECOND | L_PEND)) | (staged ? L_PEND : 0u);  // the slot bits stay for the collect
                 }
             }
         }

@@ -81,8 +81,9 @@ extern "C" int rt_render_frame_multi(rt_ctx* const* ctxs, const rt_scene* const*
         streamed = streamed && li[i].counts_done;
         for (uint32_t j = 0; j < i; j++) streamed = streamed && ctxs[i]->device != ctxs[j]->device;
     }
+    SlabJob job;
     if (streamed) {
-        rc = collect_slabs(c0, c0->d_out, a0.ctl, a0.plan, c0->out_seq, out_rgb, tunables().tile_order_reverse != 0);
+        rc = enqueue_slab_copies(c0, c0->d_out, a0.ctl, a0.plan, c0->out_seq, out_rgb, tunables().tile_order_reverse != 0, &job);
         if (rc) return rc;
     }
     // second passes (tie-break tables that had not landed) and counters, context by context
@@ -119,7 +120,10 @@ extern "C" int rt_render_frame_multi(rt_ctx* const* ctxs, const rt_scene* const*
         }
     }
     CK(c0, cudaSetDevice(c0->device));
-    if (!streamed || redone) {
+    if (streamed) {  // every context's held-back pixels are final and counted by now: the last slabs complete
+        rc = finish_slab_copies(c0, job);
+        if (rc) return rc;
+    } else {
         CK(c0, cudaMemcpyAsync(out_rgb, c0->d_out, bytes, cudaMemcpyDeviceToHost, c0->stream));
         CK(c0, cudaStreamSynchronize(c0->stream));
     }

@@ -361,7 +361,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
 #endif
     const size_t sync_bytes = off;  // everything up to here is uploaded by this call
     const size_t o_rank = take((size_t)n * 4), o_up = take(((size_t)n + std::max(ni_ref, 1u)) * 4),
-                 o_refbox = take((size_t)std::max(ni_ref, 1u) * 64);
+                 o_refbox = take((size_t)std::max(ni_ref, 1u) * 64), o_flag = take(4);
     const size_t blob_bytes = off;
     sc->o_rank = o_rank;
     sc->o_up = o_up;
@@ -405,12 +405,15 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
 
     // ---- the builder thread starts now: it knows where its tables go ------------------------------------------
     if (!ref_sync) {
+        // the flag kernels poll for the tables: down before anybody can look (device blobs are reused)
+        CK(ctx, cudaMemsetAsync(sc->d_blob + o_flag, 0, 4, ctx->stream));
+        CK(ctx, cudaStreamSynchronize(ctx->stream));
         rt_aux* const a = aux;
         rt_ctx* const c = ctx;
-        const size_t dr = o_rank, du = o_up, db = o_refbox;
+        const size_t dr = o_rank, du = o_up, db = o_refbox, df = o_flag;
         uint8_t* const dst = sc->d_blob;
         const int delay_ms = tn.aux_delay_ms;
-        a->worker = std::thread([a, c, dst, dr, du, db, delay_ms] {
+        a->worker = std::thread([a, c, dst, dr, du, db, df, delay_ms] {
             try {
                 if (delay_ms > 0) std::this_thread::sleep_for(std::chrono::milliseconds(delay_ms));
                 HostBVH bvh;
@@ -428,6 +431,9 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
                 if (e == cudaSuccess) e = cudaMemcpyAsync(dst + dr, t.rank.data(), t.rank.size() * 4, cudaMemcpyHostToDevice, c->aux_stream);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(dst + du, t.up.data(), t.up.size() * 4, cudaMemcpyHostToDevice, c->aux_stream);
                 if (e == cudaSuccess) e = cudaMemcpyAsync(dst + db, t.refbox.data(), t.refbox.size() * 4, cudaMemcpyHostToDevice, c->aux_stream);
+                // ... and then the flag kernels already running poll (stream order: the tables are there before it)
+                static const int one = 1;
+                if (e == cudaSuccess) e = cudaMemcpyAsync(dst + df, &one, 4, cudaMemcpyHostToDevice, c->aux_stream);
                 if (e == cudaSuccess) e = cudaStreamSynchronize(c->aux_stream);
                 if (e != cudaSuccess) {
                     a->err = std::string("upload of the tie-break tables failed: ") + cudaGetErrorString(e);
@@ -513,6 +519,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     }
     for (size_t i = 0; i < (size_t)MAX_BIG; i++)
         ((int32_t*)(h + o_big))[i] = i < big_world.size() ? ~(int32_t)(pid_of_world[big_world[i]] << 5) : 0;
+    *(int32_t*)(h + o_flag) = ref_sync ? 1 : 0;
     lap("primitive arrays");
 
     // traversal-tree records from the host tree: DFS pre-order numbering, left subtree first
@@ -639,6 +646,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     d.ref_up = (const uint32_t*)(sc->d_blob + o_up);
     d.ref_box = (const float4*)(sc->d_blob + o_refbox);
     d.aux_ready = 0;
+    d.aux_flag = (const int*)(sc->d_blob + o_flag);
     d.ns = n_spheres;
     d.nt = n_triangles;
     d.ni = ni_ref;

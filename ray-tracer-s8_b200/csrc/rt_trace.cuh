@@ -82,14 +82,22 @@ struct HitCtx {
     const uint32_t* rank;
     const uint32_t* ref_up;
     const float4* ref_box;
+    const int* aux_flag;
     uint32_t n;
     int aux_ready;
 };
+// Have the tie-break tables landed?  Known at launch, or polled (acquire: the tables were written before the flag).
+__device__ __forceinline__ bool aux_now(const HitCtx& hc) {
+    if (hc.aux_ready) return true;
+    int v;
+    asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(hc.aux_flag) : "memory");
+    return v != 0;
+}
 __device__ __forceinline__ HitCtx hit_ctx(const DevScene& sc) {
 #ifdef RT_AB_NO_UNSURE  // A/B build: tables assumed present (no second-pass bookkeeping in the kernel)
-    return HitCtx{sc.leaf_box, sc.rank, sc.ref_up, sc.ref_box, sc.ns + sc.nt, 1};
+    return HitCtx{sc.leaf_box, sc.rank, sc.ref_up, sc.ref_box, sc.aux_flag, sc.ns + sc.nt, 1};
 #else
-    return HitCtx{sc.leaf_box, sc.rank, sc.ref_up, sc.ref_box, sc.ns + sc.nt, sc.aux_ready};
+    return HitCtx{sc.leaf_box, sc.rank, sc.ref_up, sc.ref_box, sc.aux_flag, sc.ns + sc.nt, sc.aux_ready};
 #endif
 }
 
@@ -98,13 +106,13 @@ __device__ __forceinline__ HitCtx hit_ctx(const DevScene& sc) {
 // no longer implies that every ancestor's child box passes (e.g. d.z == 0 with o.z exactly on an ancestor's max
 // plane gives tmax = NaN and the subtree is dropped; d.x == -0.0 makes every box fail).  Such rays re-run the
 // reference's own test on every box of the leaf's ancestor chain in the REFERENCE tree, root side last.
-__device__ __noinline__ bool ref_ancestors_pass(const uint32_t* __restrict__ ref_up, const float4* __restrict__ ref_box,
-                                                uint32_t n, V3 o, V3 d, int pid) {
-    uint32_t u = __ldg(&ref_up[pid]);  // (parent << 1) | side of the leaf; its own box is tested by the caller
+__device__ __noinline__ bool ref_ancestors_pass(const uint32_t* ref_up, const float4* ref_box, uint32_t n, V3 o, V3 d, int pid) {
+    // plain loads (not the read-only path): the tables may have landed while this kernel was running
+    uint32_t u = ref_up[pid];  // (parent << 1) | side of the leaf; its own box is tested by the caller
     while (u != UP_ROOT) {
-        u = __ldg(&ref_up[n + (u >> 1)]);  // the parent's own slot in ITS parent
-        if (u == UP_ROOT) break;           // the root node's box is never tested (bvh_impl.rs:373-398)
-        const V3 lo = ld3(__ldg(&ref_box[2 * u])), hi = ld3(__ldg(&ref_box[2 * u + 1]));
+        u = ref_up[n + (u >> 1)];  // the parent's own slot in ITS parent
+        if (u == UP_ROOT) break;   // the root node's box is never tested (bvh_impl.rs:373-398)
+        const V3 lo = ld3(ref_box[2 * u]), hi = ld3(ref_box[2 * u + 1]);
         if (!ref_intersects_aabb(o, d, lo, hi)) return false;
     }
     return true;
@@ -119,7 +127,7 @@ __device__ __forceinline__ void consider(const HitCtx& hc, V3 o, V3 d, float t, 
         const bool degenerate = (d.x == 0.0f) || (d.y == 0.0f) || (d.z == 0.0f);  // +-0: inf / NaN slabs
         if (degenerate) {
             if (!ref_intersects_aabb(o, d, blo, bhi)) return;
-            if (!hc.aux_ready) flag = HIT_UNSURE;  // whether the ancestors pass is decided in the second pass
+            if (!aux_now(hc)) flag = HIT_UNSURE;  // whether the ancestors pass is decided in the second pass
             else if (!ref_ancestors_pass(hc.ref_up, hc.ref_box, hc.n, o, d, pid)) return;
         } else if (!robustly_inside(p, t, blo, bhi) && !ref_intersects_aabb(o, d, blo, bhi)) {
             return;
@@ -133,8 +141,8 @@ __device__ __forceinline__ void consider(const HitCtx& hc, V3 o, V3 d, float t, 
         take = true;
         flag |= best.pid & HIT_UNSURE;  // sticky for the rest of the query
     } else if (best.dist == dist) {
-        if (hc.aux_ready) {
-            take = __ldg(&hc.rank[pid]) < __ldg(&hc.rank[best.pid]);
+        if (aux_now(hc)) {
+            take = hc.rank[pid] < hc.rank[best.pid & ~HIT_UNSURE];  // plain loads: the tables may have landed mid-kernel
         } else {
             take = false;
             flag = HIT_UNSURE;
