@@ -309,8 +309,10 @@ cudaError_t launch_trace_bench(const DevScene& sc, int variant, bool with_big, c
     a.t_fin = (uint32_t)tn.wq_t_fin;
     a.alt = (uint32_t)tn.tb_alt;
     a.sstack_off = (uint32_t)(need / 4);
-    const size_t need_ww = need + (a.alt ? (size_t)TB_SSTACK * 768 * 4 : 0);
+    size_t need_ww = need + (a.alt == 1 ? (size_t)TB_SSTACK * 768 * 4 : 0);
+    if (a.alt == 2) need_ww = (size_t)sc.ns * 16 + (size_t)sc.nt * 64 + (size_t)sc.w4n * 112 + 16;
     if (a.alt && (need_ww + 1024 > (size_t)smem_optin || sc.lni == 0)) return cudaErrorInvalidValue;
+    if (a.alt == 2 && sc.w4n == 0) return cudaErrorInvalidValue;
     cudaError_t e = cudaMemsetAsync(ticket, 0, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
     DevScene s2 = sc;

@@ -118,10 +118,105 @@ __device__ __forceinline__ void trace_bvh_smem_stack(const DevScene& sc, const S
     }
 }
 
+// Experimental traversal for tb_ww (TbArgs.alt = 2): the 4-ary collapse of the same tree (DevScene::w4, staged in shared
+// memory in place of the binary records).  One visit = four slab tests, the hit children sorted by entry distance with
+// a 5-exchange network, the nearest entered, the others pushed far to near.
+__device__ __forceinline__ void trace_bvh4(const DevScene& sc, const SceneView& sv, const float4* w4, V3 o, V3 d, Hit& best, Ctr& ctr) {
+    best.pid = -1;
+    best.dist = 0.0f;
+    const float BIG = 1e30f;
+    float ix = fminf(fmaxf(__frcp_rn(d.x), -BIG), BIG);
+    float iy = fminf(fmaxf(__frcp_rn(d.y), -BIG), BIG);
+    float iz = fminf(fmaxf(__frcp_rn(d.z), -BIG), BIG);
+    if (!(fabsf(d.x) > 0.0f)) ix = BIG;
+    if (!(fabsf(d.y) > 0.0f)) iy = BIG;
+    if (!(fabsf(d.z) > 0.0f)) iz = BIG;
+    const float ax = fabsf(ix), ay = fabsf(iy), az = fabsf(iz);
+    const float qx = -o.x * ix, qy = -o.y * iy, qz = -o.z * iz;
+    const float slack = 4.8e-7f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 1e-30f;
+    float cull = 1001.0f;
+    const int ns = (int)sc.ns;
+    const HitCtx hc = hit_ctx(sc);
+    int stack[MAX_STACK * 3 + 1 + MAX_BIG];
+    stack[0] = TR_DONE;
+    int* top = stack + 1;
+    if (sc.ltree) *top++ = sc.w4root;
+#pragma unroll 1
+    for (int i = (int)sc.nbig - 1; i >= 0; i--) *top++ = __ldg(&sc.big_code[i]);
+    int cur = *--top;
+    const float INF = __int_as_float(0x7f800000);
+    for (;;) {
+        while (cur >= 0) {
+            const float4* r = w4 + 7 * cur;
+            const float4 a = r[0], b = r[1], c = r[2], e = r[3], f = r[4], g = r[5];
+            const int4 ch = *reinterpret_cast<const int4*>(r + 6);
+            auto slab1 = [&](float cx, float cy, float cz, float hx, float hy, float hz) -> float {
+                const float tx = fmaf(cx, ix, qx), ty = fmaf(cy, iy, qy), tz = fmaf(cz, iz, qz);
+                const float tn = fmaxf(fmaxf(fmaf(-hx, ax, tx), fmaf(-hy, ay, ty)), fmaxf(fmaf(-hz, az, tz), 0.0f));
+                const float tf = fminf(fminf(fmaf(hx, ax, tx), fmaf(hy, ay, ty)), fminf(fmaf(hz, az, tz), cull));
+                return (tn <= tf + slack) ? tn : INF;
+            };
+            float k0 = slab1(a.x, a.y, a.z, a.w, b.x, b.y);
+            float k1 = slab1(b.z, b.w, c.x, c.y, c.z, c.w);
+            float k2 = slab1(e.x, e.y, e.z, e.w, f.x, f.y);
+            float k3 = slab1(f.z, f.w, g.x, g.y, g.z, g.w);
+            int c0 = ch.x, c1 = ch.y, c2 = ch.z, c3 = ch.w;
+            auto cswap = [](float& ka, int& ca, float& kb, int& cb) {
+                const bool sw = kb < ka;
+                const float kt = sw ? kb : ka, ku = sw ? ka : kb;
+                const int ct = sw ? cb : ca, cu = sw ? ca : cb;
+                ka = kt; kb = ku; ca = ct; cb = cu;
+            };
+            cswap(k0, c0, k1, c1); cswap(k2, c2, k3, c3); cswap(k0, c0, k2, c2); cswap(k1, c1, k3, c3); cswap(k1, c1, k2, c2);
+            if (k3 < INF) *top++ = c3;
+            if (k2 < INF) *top++ = c2;
+            if (k1 < INF) *top++ = c1;
+            int nxt = c0;
+            if (!(k0 < INF)) nxt = *--top;
+            cur = nxt;
+        }
+        if (cur == TR_DONE) return;
+        const int pid = (~cur) >> 5;
+        float t = 0.0f;
+        bool cand = false;
+        if (pid < ns) {
+            const float4 s = sv.sph[pid];
+            const V3 oc = mk(x_sub(o.x, s.x), x_sub(o.y, s.y), x_sub(o.z, s.z));
+            const float bh = fmaf(oc.z, d.z, fmaf(oc.y, d.y, oc.x * d.x));
+            const float oc2 = fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x));
+            const float cf = oc2 - s.w;
+            const float disc = fmaf(bh, bh, -cf);
+            if (!(fmaf(oc2, 2e-5f, disc) < 0.0f) && !(bh > 0.0f && cf > 1e-4f * oc2)) cand = sphere_root_exact(d, oc, s.w, &t);
+        } else if (triangle_filter(sv.tri, pid - ns, o, d, cull)) {
+            const V3 ta = ld3(sv.tri[4 * (pid - ns) + 0]), ab = ld3(sv.tri[4 * (pid - ns) + 1]), ac = ld3(sv.tri[4 * (pid - ns) + 2]);
+            int stage;
+            cand = triangle_root_exact(o, d, ta, ab, ac, &t, &stage);
+        }
+        if (cand) {
+            consider(hc, o, d, t, pid, best);
+            cull = fmaf(best.dist, 1.00001f, 1e-6f);
+        }
+        cur = *--top;
+    }
+}
+
 __global__ void __launch_bounds__(768, 1) tb_ww(const DevScene sc, const TbArgs a) {
     extern __shared__ float4 smem_dyn[];
     SceneView sv;
-    tb_stage<768>(sc, sv, smem_dyn);
+    const float4* s_w4 = nullptr;
+    if (a.alt == 2) {  // geometry + the 4-ary records (in place of the binary ones)
+        float4* p = smem_dyn;
+        float4* s_sph = p;  p += sc.ns;
+        float4* s_tri = p;  p += 4 * sc.nt;
+        for (uint32_t i = threadIdx.x; i < sc.ns; i += 768) s_sph[i] = __ldg(&sc.sph[i]);
+        for (uint32_t i = threadIdx.x; i < 4 * sc.nt; i += 768) s_tri[i] = __ldg(&sc.tri[i]);
+        for (uint32_t i = threadIdx.x; i < 7 * sc.w4n; i += 768) p[i] = __ldg(&sc.w4[i]);
+        __syncthreads();
+        sv.sph2 = sc.sph2; sv.sph = s_sph; sv.tri = s_tri; sv.na = nullptr; sv.nb = nullptr; sv.nc = nullptr; sv.nd = nullptr;
+        s_w4 = p;
+    } else {
+        tb_stage<768>(sc, sv, smem_dyn);
+    }
     const int lane = threadIdx.x & 31;
     Ctr ctr;
     for (;;) {
@@ -133,7 +228,10 @@ __global__ void __launch_bounds__(768, 1) tb_ww(const DevScene sc, const TbArgs 
         if (i < a.n) {
             const float4 r0 = a.rays[2 * i], r1 = a.rays[2 * i + 1];
             Hit h;
-            if (a.alt) trace_bvh_smem_stack(sc, sv, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr, a.alt ? reinterpret_cast<int*>(smem_dyn) + a.sstack_off : nullptr);
+            if (a.alt == 2) {
+                trace_bvh4(sc, sv, s_w4, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr);
+                hit_finish(h);
+            } else if (a.alt) trace_bvh_smem_stack(sc, sv, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr, a.alt ? reinterpret_cast<int*>(smem_dyn) + a.sstack_off : nullptr);
             else trace_bvh_ch<false, true>(sc, sv, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr);  // nbig == 0 skips the list
             a.out[i] = make_int2(h.pid, h.pid >= 0 ? __float_as_int(h.dist) : 0);
         }

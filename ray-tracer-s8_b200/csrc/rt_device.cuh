@@ -61,6 +61,12 @@ struct DevScene {
     uint32_t ns, nt, ni;   // ni = inner nodes of the reference tree
 #ifdef RT_B200_EXPERIMENTS
     uint32_t big_pid[MAX_BIG];  // the big primitives' ids, as the A/B kernels read them
+    // 4-ary collapse of the host-built traversal tree (trace-bench experiment RT_B200_TB_ALT=2): 7 float4 per node:
+    // [c0.xyz h0.x][h0.yz c1.xy][c1.z h1.xyz][c2.xyz h2.x][h2.yz c3.xy][c3.z h3.xyz][4 child codes]; an empty slot has
+    // h = -1 (never hit)
+    const float4* w4;
+    uint32_t w4n;
+    int w4root;
     // the reference-topology tree in the first kernels' formats (A/B kernels under csrc/experiments/ only)
     const float4* node_a;  // [ni]    l.min.xyz, l.max.x
     const float4* node_b;  // [ni]    l.max.yz,  r.min.xy

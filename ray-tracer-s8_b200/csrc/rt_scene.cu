@@ -355,6 +355,71 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     const size_t o_sph2 = take((size_t)ns8 * 16), o_mat = take((size_t)n * 16), o_em = take((size_t)n * 4),
                  o_box = take((size_t)n * 32), o_big = take((size_t)MAX_BIG * 4);
 #ifdef RT_B200_EXPERIMENTS
+    // trace-bench experiment: the host tree collapsed to 4 children per node (greedy: open the child with the largest box)
+    std::vector<float> w4rec;
+    int32_t w4root = 0;
+    uint32_t w4n = 0;
+    if (T) {
+        auto area = [](const Box& b) {
+            const double sx = (double)b.max[0] - b.min[0], sy = (double)b.max[1] - b.min[1], sz = (double)b.max[2] - b.min[2];
+            return sx * sy + sx * sz + sy * sz;
+        };
+        struct Kid { int32_t code; Box box; };
+        struct Job { int32_t bin; uint32_t slot; };
+        std::vector<Job> jobs;
+        jobs.push_back({T->root, 0});
+        w4n = 1;
+        w4rec.assign(28, 0.0f);
+        for (size_t j = 0; j < jobs.size(); j++) {
+            const Job jb = jobs[j];
+            std::vector<Kid> kids;
+            const HostNode& hn = T->inner[(size_t)jb.bin];
+            kids.push_back({hn.left, hn.box_l});
+            kids.push_back({hn.right, hn.box_r});
+            while (kids.size() < 4) {
+                int best_k = -1;
+                double best_a = -1.0;
+                for (size_t k = 0; k < kids.size(); k++)
+                    if (kids[k].code >= 0 && area(kids[k].box) > best_a) {
+                        best_a = area(kids[k].box);
+                        best_k = (int)k;
+                    }
+                if (best_k < 0) break;
+                const HostNode& cn = T->inner[(size_t)kids[(size_t)best_k].code];
+                kids[(size_t)best_k] = {cn.left, cn.box_l};
+                kids.push_back({cn.right, cn.box_r});
+            }
+            float rec[28];
+            int32_t codes[4];
+            float cc[4][3], hh[4][3];
+            for (int k = 0; k < 4; k++) {
+                if (k < (int)kids.size()) {
+                    centre_half_of(kids[(size_t)k].box, cc[k], hh[k]);
+                    if (kids[(size_t)k].code < 0) {
+                        codes[k] = ~(int32_t)(pid_of_world[(uint32_t)~kids[(size_t)k].code] << 5);
+                    } else {
+                        codes[k] = (int32_t)w4n;
+                        jobs.push_back({kids[(size_t)k].code, w4n});
+                        w4n++;
+                        w4rec.resize((size_t)w4n * 28, 0.0f);
+                    }
+                } else {
+                    for (int a = 0; a < 3; a++) { cc[k][a] = 0.0f; hh[k][a] = -1.0f; }
+                    codes[k] = (int32_t)0x80000000;
+                }
+            }
+            for (int pr2 = 0; pr2 < 2; pr2++) {  // two boxes per three float4
+                const int k0 = 2 * pr2, k1 = 2 * pr2 + 1;
+                float* q = rec + 12 * pr2;
+                q[0] = cc[k0][0]; q[1] = cc[k0][1]; q[2] = cc[k0][2]; q[3] = hh[k0][0];
+                q[4] = hh[k0][1]; q[5] = hh[k0][2]; q[6] = cc[k1][0]; q[7] = cc[k1][1];
+                q[8] = cc[k1][2]; q[9] = hh[k1][0]; q[10] = hh[k1][1]; q[11] = hh[k1][2];
+            }
+            memcpy(rec + 24, codes, 16);
+            memcpy(w4rec.data() + (size_t)jb.slot * 28, rec, sizeof rec);
+        }
+    }
+    const size_t o_w4 = take((size_t)w4n * 112);
     const size_t nl = legacy ? (size_t)ni_ref : 0;
     const size_t o_na = take(nl * 16), o_nb = take(nl * 16), o_nc = take(nl * 16), o_nd = take(nl * 8);
     const size_t o_ca = take(nl * 16), o_cb = take(nl * 16), o_cc = take(nl * 16);
@@ -558,6 +623,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         lroot = leaf_code(~(int32_t)rest_world[0]);
     }
 #ifdef RT_B200_EXPERIMENTS
+    if (w4n) memcpy(h + o_w4, w4rec.data(), (size_t)w4n * 112);
     if (legacy) {  // the reference-topology tree in the first kernels' formats
         float* h_na = (float*)(h + o_na); float* h_nb = (float*)(h + o_nb); float* h_nc = (float*)(h + o_nc);
         int32_t* h_nd = (int32_t*)(h + o_nd);
@@ -652,6 +718,9 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     d.ni = ni_ref;
 #ifdef RT_B200_EXPERIMENTS
     for (size_t i = 0; i < (size_t)MAX_BIG; i++) d.big_pid[i] = i < big_world.size() ? pid_of_world[big_world[i]] : 0u;
+    d.w4 = (const float4*)(sc->d_blob + o_w4);
+    d.w4n = w4n;
+    d.w4root = w4root;
     d.node_a = (const float4*)(sc->d_blob + o_na);
     d.node_b = (const float4*)(sc->d_blob + o_nb);
     d.node_c = (const float4*)(sc->d_blob + o_nc);

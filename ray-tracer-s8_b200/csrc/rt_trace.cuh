@@ -328,6 +328,24 @@ __device__ __noinline__ void brute_group_slow(const HitCtx sc, const float4* sph
     }
 }
 
+// a triangle in the brute-force kernel: out of line like the spheres' slow path (K1's hot loop is the packed sphere
+// filter; everything else is kept out of its instruction stream)
+template <bool COUNT>
+__device__ __noinline__ void brute_triangle_slow(const HitCtx hc, const float4* tri, int tidx, int pid, V3 o, V3 d, Hit& best, Ctr& ctr) {
+    const V3 a = ld3(tri[4 * tidx + 0]), ab = ld3(tri[4 * tidx + 1]), ac = ld3(tri[4 * tidx + 2]);
+    if (COUNT) ctr.v[CTR_TRI_TEST]++;
+    float t;
+    int stage;
+    const bool hit = triangle_root_exact(o, d, a, ab, ac, &t, &stage);
+    if (COUNT) {
+        if (stage >= 1) ctr.v[CTR_TRI_S1]++;
+        if (stage >= 2) ctr.v[CTR_TRI_S2]++;
+        if (stage >= 3) ctr.v[CTR_TRI_S3]++;
+        if (hit) ctr.v[CTR_TRI_HIT]++;
+    }
+    if (hit) consider(hc, o, d, t, pid, best);
+}
+
 template <bool COUNT>
 __device__ __forceinline__ void trace_brute_impl(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
     best.pid = -1;
@@ -376,7 +394,8 @@ __device__ __forceinline__ void trace_brute_impl(const DevScene& sc, const Scene
         if (!(m0 < 0.0f) || weird) brute_group_slow<COUNT>(hc, sv.sph, sv.sph2, i, ns - i, o, d, weird, best, ctr);
     }
     const int nt = (int)sc.nt;
-    for (int j = 0; j < nt; j++) test_triangle<COUNT>(sc, sv.tri, j, ns + j, o, d, best, ctr);
+#pragma unroll 1
+    for (int j = 0; j < nt; j++) brute_triangle_slow<COUNT>(hc, sv.tri, j, ns + j, o, d, best, ctr);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -645,3 +645,86 @@ def test_controller_upload_to_jpeg_on_a_mesh(rt, O):
         assert_parity(np.concatenate(bands, axis=0), ref)
     finally:
         wk.close()
+
+
+def test_controller_concurrent_uploads_are_serialised(rt, O):
+    """Two /upload requests at once against the in-process controller (a ThreadingHTTPServer gives every request its own
+    thread): one rt_ctx has ONE owner at a time, so the worker serialises them; both stitched frames must be the oracle's."""
+    import io
+
+    from PIL import Image
+
+    from rt_b200 import controller, obj, slave
+    from test_host import mesh_scene_obj
+
+    data, n = mesh_scene_obj()
+    tris = obj.build_world(data, n)
+    wk = slave.Worker(0, spp=3, max_bounces=4, seed=5)
+    ready, stop = threading.Event(), threading.Event()
+    c = controller.Controller(worker=wk, width=160, height=120, divisions=20)
+    t = threading.Thread(target=controller.serve, kwargs=dict(controller=c, host="127.0.0.1", port=0, ready=ready, stop=stop), daemon=True)
+    t.start()
+    assert ready.wait(30)
+    base = f"http://127.0.0.1:{ready.port}"
+    jobs, errs = [None, None], []
+
+    def post(i):
+        try:
+            req = urllib.request.Request(f"{base}/upload/{n}/", data=data, method="POST")
+            with urllib.request.urlopen(req, timeout=120) as r:
+                jobs[i] = r.read().decode()
+        except Exception as e:  # noqa: BLE001
+            errs.append(e)
+
+    th = [threading.Thread(target=post, args=(i,)) for i in range(2)]
+    for x in th:
+        x.start()
+    for x in th:
+        x.join(180)
+    try:
+        assert not errs and all(jobs) and jobs[0] != jobs[1], (errs, jobs)
+        ref, _ = O.render_frame(None, tris, 160, 120, 3, 4, seed=5)
+        for j in jobs:
+            req = urllib.request.Request(f"{base}/poll", data=j.encode(), method="POST")
+            with urllib.request.urlopen(req, timeout=60) as r:
+                assert r.headers["Content-Type"] == "image/jpeg"
+                got = np.array(Image.open(io.BytesIO(r.read())).convert("RGB"))
+            mse = float(((got.astype(np.float64) - ref) ** 2).mean())
+            assert 10 * np.log10(255.0 ** 2 / mse) > 30.0
+        assert wk.scene_uploads == 2          # two jobs, one upload each (20 divisions share it)
+    finally:
+        stop.set()
+        t.join(30)
+        wk.close()
+
+
+def test_controller_tile_scheduler_over_devices(rt, O):
+    """f2: Controller(devices=[...]) renders the whole frame in one rt_render_frame_multi call over the listed GPUs (all
+    of them when there are several, else two contexts on device 0) and cuts it into the job's divisions; /poll
+    stitches them back.  The stitched frame is the oracle's (through the JPEG) and the slices are exact."""
+    import io
+
+    import torch
+    from PIL import Image
+
+    from rt_b200 import controller, obj, wire
+    from test_host import mesh_scene_obj
+
+    data, n = mesh_scene_obj()
+    tris = obj.build_world(data, n)
+    devs = list(range(torch.cuda.device_count())) if torch.cuda.device_count() > 1 else [0, 0]
+    c = controller.Controller(devices=devs, width=320, height=180, divisions=20, spp=4, max_bounces=4, seed=11)
+    try:
+        ref, _ = O.render_frame(None, tris, 320, 180, 4, 4, seed=11)
+        meta = wire.RenderMeta(180, 320, 20, "00000000-0000-4000-8000-00000000000b")
+        slices = c._render_all_gpus(tris, meta)
+        assert [s.division_no for s in slices] == list(range(20))
+        assert_parity(np.concatenate([s.image.reshape(9, 320, 3) for s in slices], axis=0), ref)
+        job = c.upload(data, n)
+        jpeg, is_img = c.poll(job)
+        assert is_img
+        got = np.array(Image.open(io.BytesIO(jpeg)).convert("RGB"))
+        mse = float(((got.astype(np.float64) - ref) ** 2).mean())
+        assert 10 * np.log10(255.0 ** 2 / mse) > 30.0
+    finally:
+        c.close()
