@@ -399,17 +399,24 @@ def main():
     host_frame = ctx.pinned_empty((H, W, 3)) if rank == 0 else None
     scene_bytes = scene.device_bytes
     e2e_redo = 0
+    phases = {"scene_create": [], "render_and_frame_to_host": [], "scene_destroy": [], "kernel": []}
 
     def e2e_step():
         nonlocal e2e_redo
+        ta = time.perf_counter()
         ctx.l2_flush(FLUSH_BYTES)
         sc = ctx.scene(sp, tr)                       # H2D: primitive SoA + traversal tree + materials (tie tables follow)
+        tb = time.perf_counter()
         if world == 1:
             _, s1 = ctx.render_frame(sc, params, out=host_frame, want_stats=True)   # kernel + D2H of the frame
         else:
             s1 = sched.render(sc, params, want_stats=True, out=host_frame)          # slabs stream to the host as they complete
+        tc = time.perf_counter()
         e2e_redo = max(e2e_redo, s1["redo_pixels"])
         sc.close()
+        td = time.perf_counter()
+        phases["scene_create"].append((tb - ta) * 1e3); phases["render_and_frame_to_host"].append((tc - tb) * 1e3)
+        phases["scene_destroy"].append((td - tc) * 1e3); phases["kernel"].append(s1["kernel_ms"])
 
     for _ in range(2):
         e2e_step()
@@ -501,6 +508,7 @@ def main():
                     "h2d_bytes_per_step": int(scene_bytes * world + 72 * world),
                     "d2h_bytes_per_step": int(pixels * 3 + 128 * world),
                     "pageable_destination_ms": e2e_pageable_ms, "redo_pixels_max": e2e_redo,
+                    "rank0_phases_ms_median": {k: float(np.median(v[-args.steps:])) for k, v in phases.items()},
                     "what": "rt_scene_create (ingest + upload; the reference-topology tree follows on a builder thread) + render "
                             "+ frame to pinned host memory, per step"
                             + ("; slabs stream to the host while other slabs render" if world > 1 else "")},

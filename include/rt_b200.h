@@ -189,7 +189,8 @@ int rt_render_tiles_device(rt_ctx* ctx, const rt_scene* scene, const rt_params* 
                            uint32_t tile_ranks, void* frame_dev, int sync, rt_stats* stats);
 /* The frame owner's form of the call above: renders this context's tiles into frame_dev (allocated by this context with
  * rt_frame_alloc) and, while they render, copies every slab of frame number `seq` to out_rgb as soon as ALL ranks have
- * finished it (see rt_frame_collect).  Returns with the complete frame in out_rgb (height*width*3 bytes). */
+ * finished it (see rt_frame_collect).  Returns with the complete frame in out_rgb (height*width*3 bytes); out_rgb may be
+ * NULL: the call then only waits until the frame is complete on the device. */
 int rt_render_tiles_collect(rt_ctx* ctx, const rt_scene* scene, const rt_params* params, uint32_t tile_rank,
                             uint32_t tile_ranks, void* frame_dev, uint64_t seq, uint8_t* out_rgb, size_t out_len,
                             rt_stats* stats);

@@ -298,7 +298,10 @@ int enqueue_slab_copies(rt_ctx* ctx, const uint8_t* frame_dev, const rt_frame_ct
         }
     }
     ctx->h_flag[0] = 0;
-    for (uint32_t i = 0; i < plan.slabs; i++) {
+    if (!out_rgb)  // the frame stays on the device: one kernel waits for all its slabs
+        CK(ctx, launch_wait_all_slabs(ctl->done, (unsigned long long)seq, plan.slabs, plan.tile_rows, plan.rows, plan.width,
+                                      ctx->h_flag, ctx->copy_stream));
+    for (uint32_t i = 0; out_rgb && i < plan.slabs; i++) {
         // tickets walk the frame bottom-up by default: the last slab completes first
         const uint32_t s = reverse_order ? plan.slabs - 1 - i : i;
         const unsigned long long target = (unsigned long long)seq * plan.pixels(s);
@@ -354,7 +357,7 @@ int render_and_collect(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, co
     if (streamed) {
         rc = finish_slab_copies(ctx, job);
         if (rc) return rc;
-    } else {
+    } else if (out_rgb) {
         CK(ctx, cudaMemcpyAsync(out_rgb, frame_dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
         CK(ctx, cudaStreamSynchronize(ctx->stream));
     }
@@ -580,10 +583,10 @@ int rt_render_tiles_collect(rt_ctx* ctx, const rt_scene* scene, const rt_params*
     Resolved r;
     int rc = resolve(ctx, scene, params, true, &r);
     if (rc) return rc;
-    if (!frame_dev || !out_rgb) return set_err(ctx, RT_ERR_INVALID_ARG, "frame_dev or out_rgb is NULL");
+    if (!frame_dev) return set_err(ctx, RT_ERR_INVALID_ARG, "frame_dev is NULL");
     if (tile_ranks == 0 || tile_rank >= tile_ranks || seq == 0) return set_err(ctx, RT_ERR_INVALID_ARG, "bad tile_rank/tile_ranks/seq");
     const size_t bytes = (size_t)r.p.width * r.p.height * 3;
-    if (out_len != bytes) return set_err(ctx, RT_ERR_INVALID_ARG, "out_len %zu != height*width*3 = %zu", out_len, bytes);
+    if (out_rgb && out_len != bytes) return set_err(ctx, RT_ERR_INVALID_ARG, "out_len %zu != height*width*3 = %zu", out_len, bytes);
     CK(ctx, cudaSetDevice(ctx->device));
     LaunchArgs a;
     a.row0 = 0;

@@ -21,6 +21,8 @@
 #include <mutex>
 #include <thread>
 
+#include <emmintrin.h>  // SSE2: the traversal-tree builder bins with it (x86-64 hosts; this image has no other)
+
 #include "rt_host.h"
 
 namespace rtb {
@@ -39,10 +41,12 @@ static const size_t kParallelMin = [] {
 }();
 constexpr float kEpsilon = 0.00001f;  // bvh::EPSILON (lib.rs:80)
 
-// f32::min / f32::max (NaN-ignoring) inline: libm's fminf/fmaxf are out-of-line calls under -fno-fast-math and were
-// most of the build time.
-inline float nmin(float a, float b) { return a != a ? b : (b != b ? a : (a < b ? a : b)); }
-inline float nmax(float a, float b) { return a != a ? b : (b != b ? a : (a > b ? a : b)); }
+// f32::min / f32::max inline (libm's fminf/fmaxf are out-of-line calls under -fno-fast-math and were most of the build
+// time).  Their NaN-ignoring branch is not needed: the callers validate every primitive's bounds as finite, and min / max
+// / sub / add / div-by-2 of finite or infinite values never produce a NaN here; for equal operands (and for +0 / -0)
+// these return the second one, as the previous NaN-aware form did.
+inline float nmin(float a, float b) { return a < b ? a : b; }
+inline float nmax(float a, float b) { return a > b ? a : b; }
 
 struct Bounds {
     float lo[3], hi[3];
@@ -275,10 +279,42 @@ struct Builder {
 // the DFS rank of the reference-topology tree, which is still built).  Leaves are codes ~index like above.
 // ---------------------------------------------------------------------------------------------------------
 namespace {
-struct SahRec {  // one primitive, permuted in place: centroid, world position, box
+struct alignas(16) SahRec {  // one primitive, permuted in place: centroid + world position | box min | box max (3 x 16 bytes)
     float c[3];
     uint32_t id;
-    Box b;
+    float bmin[4], bmax[4];
+};
+struct alignas(16) Bounds4 {  // lo | hi as two SSE lanes-of-four (w unused)
+    __m128 lo, hi;
+    void clear() {
+        lo = _mm_set1_ps(std::numeric_limits<float>::infinity());
+        hi = _mm_set1_ps(-std::numeric_limits<float>::infinity());
+    }
+    void join(const SahRec& r) {
+        lo = _mm_min_ps(lo, _mm_load_ps(r.bmin));
+        hi = _mm_max_ps(hi, _mm_load_ps(r.bmax));
+    }
+    void join(const Bounds4& b) {
+        lo = _mm_min_ps(lo, b.lo);
+        hi = _mm_max_ps(hi, b.hi);
+    }
+    float area() const {  // 0 for an empty box
+        alignas(16) float d[4];
+        _mm_store_ps(d, _mm_sub_ps(hi, lo));
+        if (d[0] < 0.0f || d[1] < 0.0f || d[2] < 0.0f) return 0.0f;
+        return 2.0f * (d[0] * d[1] + d[0] * d[2] + d[1] * d[2]);
+    }
+    Box box() const {
+        alignas(16) float a[4], b[4];
+        _mm_store_ps(a, lo);
+        _mm_store_ps(b, hi);
+        Box r;
+        for (int k = 0; k < 3; k++) {
+            r.min[k] = a[k];
+            r.max[k] = b[k];
+        }
+        return r;
+    }
 };
 struct SahBuilder {
     std::vector<SahRec> rec;
@@ -290,11 +326,14 @@ struct SahBuilder {
         rec.resize(b.size());
         for (size_t i = 0; i < b.size(); i++) {
             rec[i].id = (uint32_t)i;
-            rec[i].b = b[i];
-            for (int a = 0; a < 3; a++) rec[i].c[a] = 0.5f * (b[i].min[a] + b[i].max[a]);
+            for (int a = 0; a < 3; a++) {
+                rec[i].bmin[a] = b[i].min[a];
+                rec[i].bmax[a] = b[i].max[a];
+                rec[i].c[a] = 0.5f * (b[i].min[a] + b[i].max[a]);
+            }
+            rec[i].bmin[3] = rec[i].bmax[3] = 0.0f;
         }
     }
-    static float area(const Bounds& b) { return b.empty() ? 0.0f : b.area(); }
     void note_depth(uint32_t d) {
         uint32_t cur = max_depth.load(std::memory_order_relaxed);
         while (d > cur && !max_depth.compare_exchange_weak(cur, d, std::memory_order_relaxed)) {}
@@ -306,18 +345,21 @@ struct SahBuilder {
             note_depth(depth);
             return ~(int32_t)rec[lo].id;
         }
-        float cmin[3], cmax[3];
-        for (int a = 0; a < 3; a++) { cmin[a] = std::numeric_limits<float>::infinity(); cmax[a] = -cmin[a]; }
-        for (size_t i = lo; i < hi; i++)
-            for (int a = 0; a < 3; a++) {
-                cmin[a] = rec[i].c[a] < cmin[a] ? rec[i].c[a] : cmin[a];
-                cmax[a] = rec[i].c[a] > cmax[a] ? rec[i].c[a] : cmax[a];
-            }
+        // centroid bounds (the id lane rides along and is ignored)
+        __m128 cmin4 = _mm_set1_ps(std::numeric_limits<float>::infinity()), cmax4 = _mm_set1_ps(-std::numeric_limits<float>::infinity());
+        for (size_t i = lo; i < hi; i++) {
+            const __m128 c = _mm_load_ps(rec[i].c);
+            cmin4 = _mm_min_ps(cmin4, c);
+            cmax4 = _mm_max_ps(cmax4, c);
+        }
+        alignas(16) float cmin[4], cmax[4];
+        _mm_store_ps(cmin, cmin4);
+        _mm_store_ps(cmax, cmax4);
         // one pass bins all three axes; small nodes (most of them) use fewer bins, their cost is the per-node set-up
         const int nb = n <= 4 ? 2 : (n <= 16 ? 4 : (n <= 64 ? 8 : kBins));
-        Bounds bb[3][kBins];
+        Bounds4 bb[3][kBins];
         uint32_t cnt[3][kBins];
-        float scale[3];
+        alignas(16) float scale[4] = {0.0f, 0.0f, 0.0f, 0.0f};
         bool use[3];
         for (int a = 0; a < 3; a++) {
             const float ext = cmax[a] - cmin[a];
@@ -325,27 +367,37 @@ struct SahBuilder {
             scale[a] = use[a] ? (float)nb * (1.0f - 1e-6f) / ext : 0.0f;
             for (int k = 0; k < nb; k++) { bb[a][k].clear(); cnt[a][k] = 0; }
         }
+        cmin[3] = 0.0f;
+        const __m128 cm = _mm_load_ps(cmin), sc4 = _mm_load_ps(scale);
+        const __m128i top = _mm_set1_epi32(nb - 1), zero = _mm_setzero_si128();
+        auto bins_of = [&](const SahRec& r, int k[4]) {  // bin of the centroid on every axis at once
+            __m128i b = _mm_cvttps_epi32(_mm_mul_ps(_mm_sub_ps(_mm_load_ps(r.c), cm), sc4));
+            b = _mm_max_epi16(_mm_min_epi16(b, top), zero);  // bins are small non-negative ints: 16-bit lanes do
+            _mm_storeu_si128(reinterpret_cast<__m128i*>(k), b);
+        };
         auto bin_of = [&](const SahRec& r, int a) {
             int k = (int)((r.c[a] - cmin[a]) * scale[a]);
             return k < 0 ? 0 : (k >= nb ? nb - 1 : k);
         };
-        for (size_t i = lo; i < hi; i++)
+        for (size_t i = lo; i < hi; i++) {
+            int k[4];
+            bins_of(rec[i], k);
             for (int a = 0; a < 3; a++) {
                 if (!use[a]) continue;
-                const int k = bin_of(rec[i], a);
-                cnt[a][k]++;
-                bb[a][k].join(rec[i].b);
+                cnt[a][k[a]]++;
+                bb[a][k[a]].join(rec[i]);
             }
+        }
         int best_axis = -1, best_split = 0;
         float best_cost = std::numeric_limits<float>::infinity();
-        Bounds best_l, best_r;
+        Bounds4 best_l, best_r;
         best_l.clear();
         best_r.clear();
         for (int a = 0; a < 3; a++) {
             if (!use[a]) continue;
-            Bounds racc[kBins];
+            Bounds4 racc[kBins];
             size_t rcnt[kBins];
-            Bounds acc;
+            Bounds4 acc;
             acc.clear();
             size_t c = 0;
             for (int k = nb - 1; k > 0; k--) {
@@ -354,14 +406,14 @@ struct SahBuilder {
                 racc[k] = acc;
                 rcnt[k] = c;
             }
-            Bounds lacc;
+            Bounds4 lacc;
             lacc.clear();
             size_t lc = 0;
             for (int k = 0; k < nb - 1; k++) {
                 lacc.join(bb[a][k]);
                 lc += cnt[a][k];
                 if (lc == 0 || rcnt[k + 1] == 0) continue;
-                const float cost = (float)lc * area(lacc) + (float)rcnt[k + 1] * area(racc[k + 1]);
+                const float cost = (float)lc * lacc.area() + (float)rcnt[k + 1] * racc[k + 1].area();
                 if (cost < best_cost) { best_cost = cost; best_axis = a; best_split = k; best_l = lacc; best_r = racc[k + 1]; }
             }
         }
@@ -375,8 +427,8 @@ struct SahBuilder {
             mid = lo + n / 2;
             best_l.clear();
             best_r.clear();
-            for (size_t i = lo; i < mid; i++) best_l.join(rec[i].b);
-            for (size_t i = mid; i < hi; i++) best_r.join(rec[i].b);
+            for (size_t i = lo; i < mid; i++) best_l.join(rec[i]);
+            for (size_t i = mid; i < hi; i++) best_r.join(rec[i]);
         }
         const int32_t me = (int32_t)base;
         int32_t l = 0, r = 0;

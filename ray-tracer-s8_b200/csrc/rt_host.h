@@ -65,6 +65,8 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
                           int sm_count, int smem_optin, cudaStream_t stream, LaunchInfo* info);
 cudaError_t launch_wait_slab(const unsigned long long* done, unsigned long long target, unsigned int* timeout_flag,
                              cudaStream_t stream);
+cudaError_t launch_wait_all_slabs(const unsigned long long* done, unsigned long long seq, uint32_t slabs, uint32_t tile_rows,
+                                  uint32_t rows, uint32_t width, unsigned int* timeout_flag, cudaStream_t stream);
 cudaError_t launch_set_u64(unsigned long long* p, unsigned long long v, cudaStream_t stream);
 cudaError_t launch_add_counts(unsigned long long* done, const unsigned long long* add, int n, cudaStream_t stream);
 cudaError_t launch_fp32_peak(float* scratch, int sm_count, int iters, cudaStream_t stream);

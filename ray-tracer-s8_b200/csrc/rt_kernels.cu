@@ -311,34 +311,40 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                 uint32_t x = pr.width, y = 0, slot1 = 0, second = 0;
                 const uint32_t my = __popc(want & lt_mask);
                 const bool wants = (st & (L_HAVE | L_FINISHED)) == 0;
+                // (a probe for waiting list entries beside every tile ticket, so that they are rendered again as soon as the
+                // tables land instead of at the end, cost more than it saved: C3 37.7 -> 38.0 ms, 2 GPUs 19.7 -> 20.3)
+                bool redo_round = false, exhausted = false;
+                uint32_t base = 0;
                 if (ws & W_IN_TAIL) {
                     // the tail of the launch (or a second pass over a pixel list): pixel tickets, one per wanting lane
-                    uint32_t base = 0;
                     if (lane == 0) base = atomicAdd(&pr.tile_counter[1], (unsigned int)__popc(want));
                     base = __shfl_sync(FULL, base, 0);
-                    if (base >= tail_pixels) {
-                        // The tickets are gone.  Pixels that waited for the tie-break tables are rendered again by
-                        // whoever is idle, once the tables have landed: lane 0 takes up to one entry per wanting lane.
-                        uint32_t t0 = 0, n_take = 0;
-                        if (!pr.pixel_list && lane == 0) {
-                            int landed = sc.aux_ready;
-                            if (!landed) asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(landed) : "l"(sc.aux_flag) : "memory");
-                            const unsigned long long cnt = *reinterpret_cast<volatile unsigned long long*>(pr.redo_count);
-                            if (landed && cnt <= pr.redo_cap) {  // more than the list holds: the host repeats the launch
-                                for (;;) {
-                                    t0 = *reinterpret_cast<volatile unsigned int*>(&pr.tile_counter[2]);
-                                    n_take = min((uint32_t)__popc(want), (uint32_t)cnt - min((uint32_t)cnt, t0));
-                                    if (n_take == 0 || atomicCAS(&pr.tile_counter[2], t0, t0 + n_take) == t0) break;
-                                }
+                    redo_round = exhausted = base >= tail_pixels;
+                }
+                if (redo_round) {
+                    // Pixels that waited for the tie-break tables are rendered again by lanes that want work, once the
+                    // tables have landed: lane 0 takes up to one list entry per wanting lane.
+                    uint32_t t0 = 0, n_take = 0;
+                    if (!pr.pixel_list && lane == 0) {
+                        int landed = sc.aux_ready;
+                        if (!landed) asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(landed) : "l"(sc.aux_flag) : "memory");
+                        const unsigned long long cnt = *reinterpret_cast<volatile unsigned long long*>(pr.redo_count);
+                        if (landed && cnt <= pr.redo_cap) {  // more than the list holds: the host repeats the launch
+                            for (;;) {
+                                t0 = *reinterpret_cast<volatile unsigned int*>(&pr.tile_counter[2]);
+                                n_take = min((uint32_t)__popc(want), (uint32_t)cnt - min((uint32_t)cnt, t0));
+                                if (n_take == 0 || atomicCAS(&pr.tile_counter[2], t0, t0 + n_take) == t0) break;
                             }
                         }
-                        t0 = __shfl_sync(FULL, t0, 0);
-                        n_take = __shfl_sync(FULL, n_take, 0);
-                        if (n_take == 0) {
-                            ws &= ~(W_TILES_LEFT | W_IN_TAIL);
-                            if (!(st & L_HAVE)) st |= L_FINISHED;
-                            break;
-                        }
+                    }
+                    t0 = __shfl_sync(FULL, t0, 0);
+                    n_take = __shfl_sync(FULL, n_take, 0);
+                    if (n_take == 0 && exhausted) {  // the tickets are gone and nothing waits: this warp is done
+                        ws &= ~(W_TILES_LEFT | W_IN_TAIL);
+                        if (!(st & L_HAVE)) st |= L_FINISHED;
+                        break;
+                    }
+                    if (n_take) {
                         if (wants && my < n_take) {
                             uint32_t e;  // the entry is written right after its index was reserved: wait for it
                             for (uint32_t spin = 0;; spin++) {
@@ -351,8 +357,12 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
                             y = e / pr.width;
                             second = L_SECOND;
                         }
-                        base = tail_pixels;  // no ticket of the tail for anybody in this round
+                        base = tail_pixels;  // this round hands out list entries only
                     }
+                }
+                if (redo_round && base >= tail_pixels) {
+                    // (nothing else this round)
+                } else if (ws & W_IN_TAIL) {
                     const uint32_t idx = base + my;
                     if (wants && idx < tail_pixels) {
                         if (pr.pixel_list) {  // the host's second pass: exactly the listed pixels
@@ -541,6 +551,30 @@ __global__ void wait_slab_kernel(const unsigned long long* done, unsigned long l
     }
 }
 
+// All slabs of a frame at once (nobody copies them out: the frame stays on the device): thread s waits for slab s.
+__global__ void wait_all_slabs_kernel(const unsigned long long* done, unsigned long long seq, uint32_t slabs, uint32_t tile_rows,
+                                      uint32_t rows, uint32_t width, unsigned int* timeout_flag, unsigned long long max_ns) {
+    const uint32_t s = threadIdx.x;
+    if (s >= slabs) return;
+    const uint32_t r0 = min(rows, s * tile_rows * (uint32_t)TILE_H), r1 = min(rows, (s + 1) * tile_rows * (uint32_t)TILE_H);
+    const unsigned long long target = seq * (unsigned long long)(r1 - r0) * width;
+    unsigned long long t0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        unsigned long long v;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(done + s) : "memory");
+        if (v >= target) return;
+        unsigned long long t;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+        if (t - t0 > max_ns) {
+            *reinterpret_cast<volatile unsigned int*>(timeout_flag) = 1u;
+            __threadfence_system();
+            return;
+        }
+        __nanosleep(200);
+    }
+}
+
 __global__ void set_u64_kernel(unsigned long long* p, unsigned long long v) {
     __threadfence_system();
     *reinterpret_cast<volatile unsigned long long*>(p) = v;
@@ -666,6 +700,7 @@ cudaError_t preload_kernels() {
             RT_TOUCH((pick_lanes<RT_INTERSECT_BRUTE, false>(count, stage, &th)));
         }
     RT_TOUCH(wait_slab_kernel);
+    RT_TOUCH(wait_all_slabs_kernel);
     RT_TOUCH(add_counts_kernel);
     RT_TOUCH(set_u64_kernel);
     RT_TOUCH(fp32_peak_kernel);
@@ -744,6 +779,12 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
 cudaError_t launch_wait_slab(const unsigned long long* done, unsigned long long target, unsigned int* timeout_flag,
                              cudaStream_t stream) {
     wait_slab_kernel<<<1, 1, 0, stream>>>(done, target, timeout_flag, 20ull * 1000000000ull);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_wait_all_slabs(const unsigned long long* done, unsigned long long seq, uint32_t slabs, uint32_t tile_rows,
+                                  uint32_t rows, uint32_t width, unsigned int* timeout_flag, cudaStream_t stream) {
+    wait_all_slabs_kernel<<<1, MAX_SLABS, 0, stream>>>(done, seq, slabs, tile_rows, rows, width, timeout_flag, 20ull * 1000000000ull);
     return cudaGetLastError();
 }
 

@@ -465,6 +465,85 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
     if (sc.ltree) *top++ = sc.lroot;
 #pragma unroll 1
     for (int i = (int)sc.nbig - 1; WITH_BIG && i >= 0; i--) *top++ = __ldg(&sc.big_code[i]);
+#ifdef RT_AB_POSTPONE
+    // A/B build (profiles/r2_notes.md): a lane that reaches a leaf keeps it in a register and goes on descending until
+    // it holds two (or runs out of nodes), so that it does node visits instead of idling while its warp's other lanes
+    // are still between leaves; the price is a cull distance that is one leaf stale.
+    int cur = *--top;
+    int pend = 0;  // leaf codes are negative: 0 = none
+    for (;;) {
+        for (;;) {
+            if (cur >= 0) {
+                const float4* nrec = sv.na + 3 * cur;
+                const float4 a = nrec[0], b = nrec[1], c = nrec[2];
+                const int2 ch = sv.nd[cur];
+                const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
+                const float rcx = fmaf(b.z, ix, qx), rcy = fmaf(b.w, iy, qy), rcz = fmaf(c.x, iz, qz);
+                const float tl = fmaxf(fmaxf(fmaf(-a.w, ax, lcx), fmaf(-b.x, ay, lcy)), fmaxf(fmaf(-b.y, az, lcz), 0.0f));
+                const float fl = fminf(fminf(fmaf(a.w, ax, lcx), fmaf(b.x, ay, lcy)), fminf(fmaf(b.y, az, lcz), cull));
+                const float tr = fmaxf(fmaxf(fmaf(-c.y, ax, rcx), fmaf(-c.z, ay, rcy)), fmaxf(fmaf(-c.w, az, rcz), 0.0f));
+                const float fr = fminf(fminf(fmaf(c.y, ax, rcx), fmaf(c.z, ay, rcy)), fminf(fmaf(c.w, az, rcz), cull));
+                const bool hl = tl <= fl + slack;
+                const bool hr = tr <= fr + slack;
+                if (COUNT) ctr.v[CTR_SLAB] += 2;
+                const bool swap = tr < tl;
+                if (hl && hr) *top++ = swap ? ch.x : ch.y;
+                int nxt = (hr && (!hl || swap)) ? ch.y : ch.x;
+                if (!(hl || hr)) nxt = *--top;
+                cur = nxt;
+            } else if (cur != TR_DONE && pend == 0) {
+                pend = cur;
+                cur = *--top;
+            } else {
+                break;
+            }
+        }
+        if (pend == 0 && cur == TR_DONE) return;
+#pragma unroll 1
+        for (int k = 0; k < 2; k++) {
+            const int leaf = k == 0 ? pend : cur;
+            if (leaf >= 0 || leaf == TR_DONE || leaf == 0) continue;
+            const int pid = (~leaf) >> 5;
+            float t = 0.0f;
+            bool cand = false;
+            if (pid < ns) {
+                const float4 s = sv.sph[pid];
+                const V3 oc = mk(x_sub(o.x, s.x), x_sub(o.y, s.y), x_sub(o.z, s.z));
+                const float bh = fmaf(oc.z, d.z, fmaf(oc.y, d.y, oc.x * d.x));
+                const float oc2 = fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x));
+                const float cf = oc2 - s.w;
+                const float disc = fmaf(bh, bh, -cf);
+                if (COUNT) ctr.v[CTR_SPH_TEST]++;
+                if (!(fmaf(oc2, 2e-5f, disc) < 0.0f) && !(bh > 0.0f && cf > 1e-4f * oc2)) {
+                    if (COUNT) ctr.v[CTR_SPH_EXACT]++;
+                    cand = sphere_root_exact(d, oc, s.w, &t);
+                    if (COUNT && cand) ctr.v[CTR_SPH_HIT]++;
+                }
+            } else {
+                if (COUNT) ctr.v[CTR_TRI_TEST]++;
+                if (triangle_filter(sv.tri, pid - ns, o, d, cull)) {
+                    const V3 a = ld3(sv.tri[4 * (pid - ns) + 0]), ab = ld3(sv.tri[4 * (pid - ns) + 1]), ac = ld3(sv.tri[4 * (pid - ns) + 2]);
+                    int stage;
+                    cand = triangle_root_exact(o, d, a, ab, ac, &t, &stage);
+                    if (COUNT) {
+                        if (stage >= 1) ctr.v[CTR_TRI_S1]++;
+                        if (stage >= 2) ctr.v[CTR_TRI_S2]++;
+                        if (stage >= 3) ctr.v[CTR_TRI_S3]++;
+                        if (cand) ctr.v[CTR_TRI_HIT]++;
+                    }
+                }
+            }
+            if (cand) {
+                consider(hc, o, d, t, pid, best);
+                cull = fmaf(best.dist, 1.00001f, 1e-6f);
+            }
+        }
+        pend = 0;
+        if (cur == TR_DONE) return;
+        cur = *--top;
+    }
+}
+#else
     int cur = *--top;
     for (;;) {
         while (cur >= 0) {
@@ -532,6 +611,7 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
         cur = *--top;
     }
 }
+#endif
 
 // The queries as the kernels call them: the nearest hit, with Hit::unsure resolved out of the pid bit it travelled in.
 template <bool COUNT>

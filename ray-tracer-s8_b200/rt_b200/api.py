@@ -185,14 +185,16 @@ class Context:
         return st.as_dict() if want_stats else None
 
     def render_tiles_collect(self, scene: "Scene", params: RtParams, tile_rank: int, tile_ranks: int, frame_dev: int,
-                             seq: int, out: np.ndarray, want_stats=False):
+                             seq: int, out: np.ndarray | None, want_stats=False):
         """Frame owner: this rank's tiles into its frame, and the whole frame (all ranks' slabs, as they complete) into
         `out` while they render."""
-        out = self._out_buffer(out, None)
+        if out is not None:
+            out = self._out_buffer(out, None)
         st = RtStats()
         self._check(self._lib.rt_render_tiles_collect(self._h, scene._h, C.byref(params), tile_rank, tile_ranks,
-                                                      C.c_void_p(frame_dev), int(seq), out.ctypes.data_as(C.c_void_p),
-                                                      out.nbytes, C.byref(st)))
+                                                      C.c_void_p(frame_dev), int(seq),
+                                                      None if out is None else out.ctypes.data_as(C.c_void_p),
+                                                      0 if out is None else out.nbytes, C.byref(st)))
         return st.as_dict() if want_stats else None
 
     # -- shared frame (one NVLink box, one process per GPU) ----------------------------------------------

@@ -144,14 +144,15 @@ class FrameScheduler:
             if out is not None and self.rank == 0:
                 self.ctx.frame_download(buf, out)
             return st if want_stats else None
-        if self.rank == 0 and out is not None:
+        if self.rank == 0 and self.world > 1:
+            # own tiles + the whole frame: into `out` slab by slab, or (out None) just complete on the device
             st = self.ctx.render_tiles_collect(scene, params, 0, self.world, buf, seq, out, want_stats=True)
         else:
             if self.rank != 0:
                 self.ctx.frame_wait_consumed(buf, self._frame_bytes, seq - 1)   # device-side, before the kernel
             st = self.ctx.render_tiles_device(scene, params, self.rank, self.world, buf, sync=True, want_stats=True)
-            if self.rank == 0 and self.world > 1:
-                self.ctx.frame_collect(buf, params, seq, None)   # wait for the other ranks' slabs
+            if out is not None and self.rank == 0:
+                self.ctx.frame_download(buf, out)
         return st if want_stats else None
 
     def download(self, out: np.ndarray) -> np.ndarray:
