@@ -129,6 +129,7 @@ struct LaunchArgs {
     uint32_t out_row0 = 0;
     rt_frame_ctl* ctl = nullptr;  // its control block (nullable: no completion counting)
     SlabPlan plan;
+    bool stream = false;          // the frame goes to the host slab by slab while it renders (stage + counters wanted)
     const unsigned int* pixel_list = nullptr;  // redo launch: render exactly these pixels (y * width + x)
     uint32_t list_count = 0;
 };
@@ -150,6 +151,7 @@ struct SlabJob {
     uint8_t* out = nullptr;       // caller's destination
     uint8_t* pinned = nullptr;    // where the device copies go (== out when out is pinned)
     bool reverse = false;
+    uint32_t host_done = 0;       // pageable path: slabs already copied on to `out`
 };
 int enqueue_slab_copies(rt_ctx* ctx, const uint8_t* frame_dev, const rt_frame_ctl* ctl, const SlabPlan& plan, uint64_t seq,
                         uint8_t* out_rgb, bool reverse_order, SlabJob* job);

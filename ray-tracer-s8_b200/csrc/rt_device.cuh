@@ -106,6 +106,7 @@ struct DevParams {
     // with a system-scope fence so the frame owner may copy a slab out as soon as its count is complete
     unsigned long long* done;
     uint32_t slab_tile_rows;
+    int stage_hint;              // the caller will stream slabs to the host: use the output stage even for a single rank
     unsigned long long* counters;  // NUM_COUNTERS
     // second pass: a pixel whose queries needed the tie-break tables before they had landed is appended to redo_list
     // (REDO_VALID | (y * width + x); the list is zeroed before the launch) and NOT added to `done`; redo_slab[slab] counts

@@ -484,7 +484,7 @@ def test_c3_full_size_tile_partition(ctx, rt):
     reproduce the single-rank frame; ray counts add up."""
     c = rt.scenes.CONFIGS["C3"]
     sp, tr = rt.scenes.config_scene("C3")
-    sc = ctx.scene(sp, tr)
+    sc = ctx.scene(sp, tr).wait_ready()      # ray counts are compared: no pixel may be traced twice
     p = rt.make_params(c["width"], c["height"], spp=4, max_bounces=c["max_bounces"])
     whole, sw = ctx.render_frame(sc, p, want_stats=True)
     nbytes = c["width"] * c["height"] * 3
