@@ -299,14 +299,21 @@ int enqueue_slab_copies(rt_ctx* ctx, const uint8_t* frame_dev, const rt_frame_ct
         }
     }
     ctx->h_flag[0] = 0;
-    if (!out_rgb)  // the frame stays on the device: one kernel waits for all its slabs
+    job->ctl = ctl;
+    const bool by_value = ctx->stream_wait_value64 != nullptr;
+    if (!out_rgb && !by_value)  // the frame stays on the device: one kernel waits for all its slabs
         CK(ctx, launch_wait_all_slabs(ctl->done, (unsigned long long)seq, plan.slabs, plan.tile_rows, plan.rows, plan.width,
                                       ctx->h_flag, ctx->copy_stream));
-    for (uint32_t i = 0; out_rgb && i < plan.slabs; i++) {
+    for (uint32_t i = 0; (out_rgb || by_value) && i < plan.slabs; i++) {
         // tickets walk the frame bottom-up by default: the last slab completes first
         const uint32_t s = reverse_order ? plan.slabs - 1 - i : i;
         const unsigned long long target = (unsigned long long)seq * plan.pixels(s);
-        CK(ctx, launch_wait_slab(&ctl->done[s], target, ctx->h_flag, ctx->copy_stream));
+        if (by_value) {  // CU_STREAM_WAIT_VALUE_GEQ = 0: the stream itself waits, no SM involved
+            const int wr = ctx->stream_wait_value64((void*)ctx->copy_stream, (unsigned long long)(uintptr_t)&ctl->done[s], target, 0u);
+            if (wr != 0) return set_err(ctx, RT_ERR_CUDA, "cuStreamWaitValue64 failed (%d)", wr);
+        } else {
+            CK(ctx, launch_wait_slab(&ctl->done[s], target, ctx->h_flag, ctx->copy_stream));
+        }
         if (out_rgb) {
             const size_t off = (size_t)plan.first_row(s) * plan.width * 3;
             const size_t nb = (size_t)plan.row_count(s) * plan.width * 3;
@@ -336,7 +343,16 @@ static int host_copy_slabs(rt_ctx* ctx, const SlabJob& job, uint32_t first, bool
             (void)cudaGetLastError();
             if (!landed) break;
         } else {
-            CK(ctx, cudaEventSynchronize(ctx->slab_events[s]));
+            const auto t0 = std::chrono::steady_clock::now();
+            while (cudaEventQuery(ctx->slab_events[s]) != cudaSuccess) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+                    (void)cudaGetLastError();
+                    *done_out = i;
+                    return RT_OK;  // finish_slab_copies' drain reports the timeout
+                }
+                std::this_thread::yield();
+            }
+            (void)cudaGetLastError();
         }
         if (ctx->h_flag[0]) break;
         const size_t off = (size_t)job.plan.first_row(s) * job.plan.width * 3;
@@ -346,13 +362,39 @@ static int host_copy_slabs(rt_ctx* ctx, const SlabJob& job, uint32_t first, bool
     return RT_OK;
 }
 
+// A stream that waits by value has no time limit of its own: give up after 20 s by satisfying every wait from the side.
+static int drain_copy_stream(rt_ctx* ctx, const SlabJob& job) {
+    const auto t0 = std::chrono::steady_clock::now();
+    for (;;) {
+        const cudaError_t q = cudaStreamQuery(ctx->copy_stream);
+        if (q == cudaSuccess) break;
+        if (q != cudaErrorNotReady) return set_err(ctx, RT_ERR_CUDA, "copy stream: %s", cudaGetErrorString(q));
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+            ctx->h_flag[0] = 1;
+            if (job.ctl) {
+                unsigned long long* fill = ctx->h_ctr;  // pinned scratch: RT_CTR_SLOTS >= MAX_SLABS entries
+                for (int i = 0; i < MAX_SLABS; i++) fill[i] = 0x7fffffffffffffffull;
+                cudaMemcpyAsync(const_cast<unsigned long long*>(job.ctl->done), fill, MAX_SLABS * sizeof(unsigned long long),
+                                cudaMemcpyHostToDevice, ctx->aux_stream);
+                cudaStreamSynchronize(ctx->aux_stream);
+            }
+            cudaStreamSynchronize(ctx->copy_stream);
+            break;
+        }
+        std::this_thread::yield();
+    }
+    (void)cudaGetLastError();
+    return RT_OK;
+}
+
 int finish_slab_copies(rt_ctx* ctx, const SlabJob& job) {
     if (job.out && job.pinned != job.out) {
         uint32_t done = 0;
         const int rc = host_copy_slabs(ctx, job, job.host_done, false, &done);
         if (rc) return rc;
     }
-    CK(ctx, cudaStreamSynchronize(ctx->copy_stream));
+    const int rc = drain_copy_stream(ctx, job);
+    if (rc) return rc;
     if (ctx->h_flag[0]) return set_err(ctx, RT_ERR_TIMEOUT, "a slab of the frame did not complete within 20 s");
     return RT_OK;
 }
@@ -480,6 +522,16 @@ int rt_init(int device, rt_ctx** out) {
     ctx->h_flag[0] = 0;
     // load the module and resolve every kernel now: the first division of a job must not pay the lazy load
     CKI(preload_kernels());
+    {   // stream memory operations, if this driver and device have them (64-bit waits)
+        int can64 = 0;
+        void* fn = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaDeviceGetAttribute(&can64, static_cast<cudaDeviceAttr>(122) /* CU_DEVICE_ATTRIBUTE_CAN_USE_64_BIT_STREAM_MEM_OPS */, device) == cudaSuccess && can64 &&
+            cudaGetDriverEntryPoint("cuStreamWaitValue64", &fn, cudaEnableDefault, &qr) == cudaSuccess &&
+            qr == cudaDriverEntryPointSuccess && fn && !std::getenv("RT_B200_NO_STREAM_WAIT"))
+            ctx->stream_wait_value64 = reinterpret_cast<int (*)(void*, unsigned long long, unsigned long long, unsigned int)>(fn);
+        (void)cudaGetLastError();
+    }
 #undef CKI
     *out = ctx;
     return RT_OK;

@@ -41,6 +41,10 @@ struct rt_ctx {
     unsigned long long* h_ctr = nullptr;  // pinned mirror
     unsigned int* d_redo = nullptr;       // pixels to render again once the tie-break tables are up (REDO_CAP entries)
     unsigned int* h_flag = nullptr;       // pinned + mapped: [0] a slab wait timed out
+    // cuStreamWaitValue64 (driver entry point, resolved in rt_init; null: not available → wait kernels): a stream waits
+    // for a counter in device memory without occupying an SM — the render kernel leaves no room for a waiting kernel
+    // (1024 threads x 64 registers = the whole register file of every SM)
+    int (*stream_wait_value64)(void* stream, unsigned long long addr, unsigned long long value, unsigned int flags) = nullptr;
     uint8_t* h_frame = nullptr;           // pinned staging for frames streamed to a pageable destination
     size_t h_frame_bytes = 0;
     std::vector<cudaEvent_t> slab_events; // one per slab, for the pageable path's per-slab host copies
@@ -152,6 +156,7 @@ struct SlabJob {
     uint8_t* pinned = nullptr;    // where the device copies go (== out when out is pinned)
     bool reverse = false;
     uint32_t host_done = 0;       // pageable path: slabs already copied on to `out`
+    const rt_frame_ctl* ctl = nullptr;
 };
 int enqueue_slab_copies(rt_ctx* ctx, const uint8_t* frame_dev, const rt_frame_ctl* ctl, const SlabPlan& plan, uint64_t seq,
                         uint8_t* out_rgb, bool reverse_order, SlabJob* job);

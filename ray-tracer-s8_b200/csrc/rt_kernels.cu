@@ -8,7 +8,7 @@
 // takes the next pixel of the warp's tile instead of idling until the slowest pixel of the tile is done.
 //
 //   * scene staging: geometry + traversal tree are one contiguous image in the scene blob and reach shared memory
-//     by ONE cp.async.bulk per CTA, completion on an mbarrier (UBLKCP in SASS); one 768-thread CTA per SM, so one
+//     by ONE cp.async.bulk per CTA, completion on an mbarrier (UBLKCP in SASS); one 1024-thread CTA per SM, so one
 //     copy of the scene per SM and the rest of the 228 KB left to L1 for the traversal stacks
 //   * output: finished pixels are staged in a per-warp shared-memory tile; a complete tile leaves as twelve
 //     8-byte row vectors (the frame may be peer memory: these are the NVLink stores of the fused render + gather)
@@ -27,6 +27,11 @@
 
 namespace rtb {
 
+#ifdef RT_AB_TPB
+constexpr int SMEM_TPB = RT_AB_TPB;  // A/B build: another CTA size for the shared-memory shape
+#else
+constexpr int SMEM_TPB = 1024;
+#endif
 constexpr int OUT_SLOTS = 4;                        // tiles a warp can have in flight in its output stage
 constexpr int TILE_PIX = TILE_W * TILE_H;
 constexpr int TILE_BYTES = TILE_PIX * 3;
@@ -644,7 +649,7 @@ const Tunables& tunables() {
 // ---------------------------------------------------------------------------------------------
 typedef void (*KernelFn)(const DevScene, const DevCamera, const DevParams);
 
-// instantiations: the product shapes (one 768-thread CTA per SM with the scene in shared memory; 4 x 256 threads at
+// instantiations: the product shapes (one 1024-thread CTA per SM with the scene in shared memory; 4 x 256 threads at
 // 64 registers when the scene is read through L1/L2 and the BVH kernel is latency bound — 65,536 spheres 3.13 → 2.84 ms)
 // with and without the output stage, and the instrumented (COUNT) form at 3 x 256 threads
 template <int ISECT, bool SMEM>
@@ -654,9 +659,11 @@ static KernelFn pick_lanes(bool count, bool stage, int* threads) {
         return (KernelFn)render_kernel_lanes<ISECT, SMEM, true, false, 3, THREADS>;
     }
     if (SMEM) {
-        *threads = 768;
-        return stage ? (KernelFn)render_kernel_lanes<ISECT, SMEM, false, true, 1, 768>
-                     : (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 1, 768>;
+        // one CTA per SM, as many warps as a CTA can have: C3 40.6 ms at 640 threads, 38.0 at 768 (74 registers), 37.65 at
+        // 896 (72), 36.7 at 1024 (64 registers, 48 bytes of spills) — profiles/r2_ab_cta_size.log
+        *threads = SMEM_TPB;
+        return stage ? (KernelFn)render_kernel_lanes<ISECT, SMEM, false, true, 1, SMEM_TPB>
+                     : (KernelFn)render_kernel_lanes<ISECT, SMEM, false, false, 1, SMEM_TPB>;
     }
     *threads = THREADS;
     if (ISECT == RT_INTERSECT_BVH)
@@ -705,9 +712,9 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
         if (launch_experiment(sc, cam, pr, isect, count, sm_count, smem_optin, stream, info, &ee)) return ee;
     }
 #endif
-    const size_t static_smem = 24 * OUT_SLOTS * (TILE_BYTES + 20) + 64;
+    const size_t static_smem = (SMEM_TPB / 32) * (OUT_SLOTS * (TILE_BYTES + 16) + 4) + 64;
     const size_t need = scene_smem_bytes(sc, isect);
-    // Stage the scene in shared memory when one 768-thread CTA per SM fits with it (scenes up to ~200 KB); larger
+    // Stage the scene in shared memory when one 1024-thread CTA per SM fits with it (scenes up to ~200 KB); larger
     // scenes are read through L1/L2 (measured on the C5 sweep, profiles/r1_c5_sweep.log)
     if (info) info->counts_done = true;
     bool smem = !count ? (need + static_smem + 1024 <= (size_t)smem_optin)
