@@ -41,6 +41,9 @@ __device__ __forceinline__ void tb_stage(const DevScene& sc, SceneView& sv, floa
     __syncthreads();
     sv.sph2 = sc.sph2;
     sv.sph = s_sph; sv.tri = s_tri; sv.na = s_na; sv.nb = nullptr; sv.nc = nullptr; sv.nd = s_nd;
+    // the product's traversal (64-byte records, rt_device.cuh) reads its nodes from global memory here
+    sv.nodes_s = 0;
+    sv.nodes_g = reinterpret_cast<const char*>(sc.lnode);
 }
 
 // Experimental traversal for tb_ww (TbArgs.alt = 1): the product's traversal with the stack in shared memory
@@ -232,7 +235,7 @@ __global__ void __launch_bounds__(768, 1) tb_ww(const DevScene sc, const TbArgs 
                 trace_bvh4(sc, sv, s_w4, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr);
                 hit_finish(h);
             } else if (a.alt) trace_bvh_smem_stack(sc, sv, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr, a.alt ? reinterpret_cast<int*>(smem_dyn) + a.sstack_off : nullptr);
-            else trace_bvh_ch<false, true>(sc, sv, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr);  // nbig == 0 skips the list
+            else trace_bvh_ch<false, true, false>(sc, sv, mk(r0.x, r0.y, r0.z), mk(r0.w, r1.x, r1.y), h, ctr);  // nbig == 0 skips the list
             a.out[i] = make_int2(h.pid, h.pid >= 0 ? __float_as_int(h.dist) : 0);
         }
         __syncwarp();

@@ -101,7 +101,7 @@ __device__ __forceinline__ void centre_half_dev(const B6& b, float c[3], float h
 __global__ void refit(const unsigned long long* __restrict__ keys, const float* __restrict__ boxes,
                       const uint32_t* __restrict__ pid_of, int n, const int2* __restrict__ child,
                       const int* __restrict__ parent, unsigned int* __restrict__ arrived, B6* nbox,
-                      float4* __restrict__ lnode_abc, int2* __restrict__ lnode_d) {
+                      float4* __restrict__ lnode, float4* __restrict__ lnode_abc, int2* __restrict__ lnode_d) {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     int node = parent[n - 1 + p];
@@ -137,10 +137,18 @@ __global__ void refit(const unsigned long long* __restrict__ keys, const float* 
         float lc[3], lh[3], rc[3], rh[3];
         centre_half_dev(bl, lc, lh);
         centre_half_dev(br, rc, rh);
-        lnode_abc[3 * (size_t)node + 0] = make_float4(lc[0], lc[1], lc[2], lh[0]);
-        lnode_abc[3 * (size_t)node + 1] = make_float4(lh[1], lh[2], rc[0], rc[1]);
-        lnode_abc[3 * (size_t)node + 2] = make_float4(rc[2], rh[0], rh[1], rh[2]);
-        lnode_d[node] = make_int2(cl, cr);
+        lnode[4 * (size_t)node + 0] = make_float4(lc[0], lc[1], lc[2], lh[0]);
+        lnode[4 * (size_t)node + 1] = make_float4(lh[1], lh[2], rc[0], rc[1]);
+        lnode[4 * (size_t)node + 2] = make_float4(rc[2], rh[0], rh[1], rh[2]);
+        // inner children by the byte offset of their record (rt_device.cuh)
+        reinterpret_cast<int4*>(lnode)[4 * (size_t)node + 3] =
+            make_int4(cl >= 0 ? cl * NODE_BYTES : cl, cr >= 0 ? cr * NODE_BYTES : cr, 0, 0);
+        if (lnode_abc) {  // experiment builds keep the index-coded form as well
+            lnode_abc[3 * (size_t)node + 0] = make_float4(lc[0], lc[1], lc[2], lh[0]);
+            lnode_abc[3 * (size_t)node + 1] = make_float4(lh[1], lh[2], rc[0], rc[1]);
+            lnode_abc[3 * (size_t)node + 2] = make_float4(rc[2], rh[0], rh[1], rh[2]);
+            lnode_d[node] = make_int2(cl, cr);
+        }
         B6 u;
         for (int a = 0; a < 3; a++) {
             u.lo[a] = fminf(bl.lo[a], br.lo[a]);
@@ -227,9 +235,10 @@ void free_device_build(DeviceBuild* b) {
 }
 
 // boxes: n x (min xyz, max xyz) of the primitives the tree covers (host); pid_of: their primitive ids (host).
-// Writes n - 1 node records to lnode_abc / lnode_d (device); the root is node 0.  *depth_out = deepest leaf.
+// Writes n - 1 node records to lnode (device; and to legacy_abc / legacy_d when given); the root is node 0.
+// *depth_out = deepest leaf.
 cudaError_t build_lbvh_device(DeviceBuild* buf, const float* h_boxes, const uint32_t* h_pid_of, uint32_t n,
-                              float4* lnode_abc, int2* lnode_d, uint32_t* depth_out, cudaStream_t stream) {
+                              float4* lnode, float4* lnode_abc, int2* lnode_d, uint32_t* depth_out, cudaStream_t stream) {
     if (n < 2) return cudaErrorInvalidValue;
     // centroid bounds on the host: one pass over data the host already holds
     float cmin[3] = {3.0e38f, 3.0e38f, 3.0e38f}, cmax[3] = {-3.0e38f, -3.0e38f, -3.0e38f};
@@ -284,7 +293,7 @@ cudaError_t build_lbvh_device(DeviceBuild* buf, const float* h_boxes, const uint
     morton_keys<<<G, T, 0, stream>>>(d_boxes, n, lo, sc, k0);
     if ((e = cub::DeviceRadixSort::SortKeys(m + o_sort, sort_bytes, k0, k1, (int)n, 0, 62, stream)) != cudaSuccess) return e;
     karras_nodes<<<G, T, 0, stream>>>(k1, (int)n, d_child, d_parent);
-    refit<<<G, T, 0, stream>>>(k1, d_boxes, d_pid, (int)n, d_child, d_parent, d_arr, d_nbox, lnode_abc, lnode_d);
+    refit<<<G, T, 0, stream>>>(k1, d_boxes, d_pid, (int)n, d_child, d_parent, d_arr, d_nbox, lnode, lnode_abc, lnode_d);
     leaf_depths<<<G, T, 0, stream>>>(d_parent, (int)n, d_arr + n);
     unsigned int depth = 0;
     if ((e = cudaMemcpyAsync(&depth, d_arr + n, 4, cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;

@@ -57,7 +57,7 @@ struct DeviceBuild {
 };
 void free_device_build(DeviceBuild* b);
 cudaError_t build_lbvh_device(DeviceBuild* buf, const float* h_boxes, const uint32_t* h_pid_of, uint32_t n,
-                              float4* lnode_abc, int2* lnode_d, uint32_t* depth_out, cudaStream_t stream);
+                              float4* lnode, float4* legacy_abc, int2* legacy_d, uint32_t* depth_out, cudaStream_t stream);
 
 // rt_kernels.cu
 cudaError_t preload_kernels();

@@ -171,9 +171,9 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
 
     SceneView sv;
     if (SMEM) {
-        // image layout = blob layout: sph | tri | lnode_a | lnode_d (BVH) or sph | tri + sph2 (brute force)
+        // image layout = blob layout: sph | tri | lnode (BVH) or sph | tri + sph2 (brute force)
         const uint32_t geom = sc.ns * 16u + sc.nt * 64u;
-        const uint32_t rest = (ISECT == RT_INTERSECT_BVH) ? sc.lni * 48u + ((sc.lni * 8u + 15u) & ~15u)
+        const uint32_t rest = (ISECT == RT_INTERSECT_BVH) ? sc.lni * (uint32_t)NODE_BYTES
                                                           : ((sc.ns + 7u) & ~7u) * 16u;
         uint8_t* base = reinterpret_cast<uint8_t*>(smem_dyn);
         if (threadIdx.x == 0) mbar_init(&s_bar, 1);
@@ -190,12 +190,14 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
         sv.sph = reinterpret_cast<const float4*>(base);
         sv.tri = reinterpret_cast<const float4*>(base + sc.ns * 16u);
         sv.sph2 = reinterpret_cast<const float4*>(base + geom);
-        sv.na = reinterpret_cast<const float4*>(base + geom);
-        sv.nd = reinterpret_cast<const int2*>(base + geom + sc.lni * 48u);
-        sv.nb = nullptr; sv.nc = nullptr;
+        sv.na = nullptr; sv.nb = nullptr; sv.nc = nullptr; sv.nd = nullptr;
+        sv.nodes_s = (uint32_t)__cvta_generic_to_shared(base + geom);
+        sv.nodes_g = nullptr;
     } else {
         sv.sph2 = sc.sph2;
-        sv.sph = sc.sph; sv.tri = sc.tri; sv.na = sc.lnode_a; sv.nb = nullptr; sv.nc = nullptr; sv.nd = sc.lnode_d;
+        sv.sph = sc.sph; sv.tri = sc.tri; sv.na = nullptr; sv.nb = nullptr; sv.nc = nullptr; sv.nd = nullptr;
+        sv.nodes_s = 0;
+        sv.nodes_g = reinterpret_cast<const char*>(sc.lnode);
     }
     if (STAGE && lane < OUT_SLOTS) {
         s_key[warp][lane] = KEY_FREE;
@@ -204,6 +206,18 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
         if (lane == 0) s_cnt[warp] = 0xffu << 24;  // no slab yet
     }
     if (SMEM) mbar_wait(&s_bar, 0);  // every thread observes the completed transaction itself
+    if (SMEM && ISECT == RT_INTERSECT_BVH) {
+        // inner-node child codes arrive as byte offsets from record 0: make them shared-window addresses, once
+        for (uint32_t i = threadIdx.x; i < sc.lni; i += TPB) {
+            int2* ch = reinterpret_cast<int2*>(reinterpret_cast<uint8_t*>(smem_dyn) + sc.ns * 16u + sc.nt * 64u +
+                                               i * (uint32_t)NODE_BYTES + 48u);
+            int2 v = *ch;
+            if (v.x >= 0) v.x += (int)sv.nodes_s;
+            if (v.y >= 0) v.y += (int)sv.nodes_s;
+            *ch = v;
+        }
+        __syncthreads();
+    }
     __syncwarp();
 
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -411,7 +425,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
             }
             Hit h;
             if (ISECT == RT_INTERSECT_BRUTE) trace_brute<COUNT>(sc, sv, o, d, h, ctr);
-            else trace_bvh_ch<COUNT>(sc, sv, o, d, h, ctr);
+            else trace_bvh_ch<COUNT, true, SMEM>(sc, sv, o, d, h, ctr);
             if (h.unsure) st |= L_REDO;
 
             bool done;
@@ -675,7 +689,7 @@ static KernelFn pick_lanes(bool count, bool stage, int* threads) {
 
 size_t scene_smem_bytes(const DevScene& sc, int isect) {
     size_t b = (size_t)sc.ns * 16 + (size_t)sc.nt * 64;
-    if (isect == RT_INTERSECT_BVH) b += (size_t)sc.lni * 48 + (((size_t)sc.lni * 8 + 15) & ~(size_t)15);
+    if (isect == RT_INTERSECT_BVH) b += (size_t)sc.lni * NODE_BYTES;
     else b += (size_t)((sc.ns + 7u) & ~7u) * 16;  // pair-packed spheres
     return b;
 }

@@ -349,9 +349,11 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         off = align_up(off + bytes, 256);
         return o;
     };
-    const size_t o_sph = 0, o_tri = o_sph + (size_t)n_spheres * 16, o_la = o_tri + (size_t)n_triangles * 64,
-                 o_ld = o_la + (size_t)lni * 48;
-    off = align_up(o_ld + align_up((size_t)lni * 8, 16), 256);
+    const size_t o_sph = 0, o_tri = o_sph + (size_t)n_spheres * 16, o_ln = o_tri + (size_t)n_triangles * 64;
+    off = align_up(o_ln + (size_t)lni * NODE_BYTES, 256);
+#ifdef RT_B200_EXPERIMENTS
+    const size_t o_la = take((size_t)lni * 48), o_ld = take((size_t)lni * 8);
+#endif
     const size_t o_sph2 = take((size_t)ns8 * 16), o_mat = take((size_t)n * 16), o_em = take((size_t)n * 4),
                  o_box = take((size_t)n * 32), o_big = take((size_t)MAX_BIG * 4);
 #ifdef RT_B200_EXPERIMENTS
@@ -517,7 +519,6 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     }
 
     // ---- fill the staging copy ------------------------------------------------------------------------------------
-    memset(h + o_ld, 0, align_up((size_t)lni * 8, 16));  // the image's tail padding is copied to shared memory
     float* h_sph = (float*)(h + o_sph);
     float* h_tri = (float*)(h + o_tri);
     float* h_mat = (float*)(h + o_mat);
@@ -593,8 +594,12 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     if (device_tree) {
         lroot = 0;  // nodes 0 .. n-2 are written on the device after the upload; the root is node 0
     } else if (T) {
+        float* ln = (float*)(h + o_ln);
+        int32_t* lc = (int32_t*)(h + o_ln);  // the same records: words 12, 13 are the child codes
+#ifdef RT_B200_EXPERIMENTS
         float* la = (float*)(h + o_la);
         int32_t* ld = (int32_t*)(h + o_ld);
+#endif
         struct Item { int32_t code; uint32_t parent; int side; };
         std::vector<Item> todo;
         uint32_t next = 0;
@@ -603,20 +608,33 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             const Item it = todo.back();
             todo.pop_back();
             const uint32_t me = next++;
-            if (it.side < 0) lroot = (int32_t)me;
-            else ld[2 * (size_t)it.parent + it.side] = (int32_t)me;
+            if (it.side < 0) lroot = (int32_t)me * NODE_BYTES;
+            else lc[16 * (size_t)it.parent + 12 + it.side] = (int32_t)me * NODE_BYTES;
+#ifdef RT_B200_EXPERIMENTS
+            if (it.side >= 0) ld[2 * (size_t)it.parent + it.side] = (int32_t)me;
+#endif
             const HostNode& hn = T->inner[(size_t)it.code];
             float lcn[3], lhh[3], rcn[3], rhh[3];
             centre_half_of(hn.box_l, lcn, lhh);
             centre_half_of(hn.box_r, rcn, rhh);
-            float* pa = la + 12 * (size_t)me;
+            float* pa = ln + 16 * (size_t)me;
             pa[0] = lcn[0]; pa[1] = lcn[1]; pa[2] = lcn[2]; pa[3] = lhh[0];
             pa[4] = lhh[1]; pa[5] = lhh[2]; pa[6] = rcn[0]; pa[7] = rcn[1];
             pa[8] = rcn[2]; pa[9] = rhh[0]; pa[10] = rhh[1]; pa[11] = rhh[2];
+            lc[16 * (size_t)me + 14] = 0; lc[16 * (size_t)me + 15] = 0;
+#ifdef RT_B200_EXPERIMENTS
+            memcpy(la + 12 * (size_t)me, pa, 48);
+#endif
             const int32_t kids[2] = {hn.left, hn.right};
             for (int side = 1; side >= 0; side--) {  // push right first so the left subtree is numbered first
-                if (kids[side] < 0) ld[2 * (size_t)me + side] = leaf_code(kids[side]);
-                else todo.push_back(Item{kids[side], me, side});
+                if (kids[side] < 0) {
+                    lc[16 * (size_t)me + 12 + side] = leaf_code(kids[side]);
+#ifdef RT_B200_EXPERIMENTS
+                    ld[2 * (size_t)me + side] = leaf_code(kids[side]);
+#endif
+                } else {
+                    todo.push_back(Item{kids[side], me, side});
+                }
             }
         }
     } else if (ltree) {  // a single primitive in the tree: the root is its leaf
@@ -682,7 +700,13 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         }
         uint32_t depth = 0;
         e = build_lbvh_device(&ctx->dbuild, dev_boxes.data(), dev_pid.data(), (uint32_t)dev_pid.size(),
-                              (float4*)(sc->d_blob + o_la), (int2*)(sc->d_blob + o_ld), &depth, ctx->stream);
+                              (float4*)(sc->d_blob + o_ln),
+#ifdef RT_B200_EXPERIMENTS
+                              (float4*)(sc->d_blob + o_la), (int2*)(sc->d_blob + o_ld),
+#else
+                              nullptr, nullptr,
+#endif
+                              &depth, ctx->stream);
         if (e != cudaSuccess || depth > (uint32_t)MAX_STACK) {
             give_back();
             if (e != cudaSuccess) return set_err(ctx, RT_ERR_CUDA, "device BVH build failed: %s", cudaGetErrorString(e));
@@ -697,8 +721,11 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     DevScene& d = sc->dev;
     d.sph = (const float4*)(sc->d_blob + o_sph);
     d.tri = (const float4*)(sc->d_blob + o_tri);
+    d.lnode = (const float4*)(sc->d_blob + o_ln);
+#ifdef RT_B200_EXPERIMENTS
     d.lnode_a = (const float4*)(sc->d_blob + o_la);
     d.lnode_d = (const int2*)(sc->d_blob + o_ld);
+#endif
     d.sph2 = (const float4*)(sc->d_blob + o_sph2);
     d.lni = lni;
     d.lroot = lroot;

@@ -41,11 +41,18 @@ struct SceneView {
     const float4* sph2;  // brute-force kernel only
     const float4* sph;
     const float4* tri;
-    const float4* na;
+    const float4* na;   // experiment kernels: index-coded node arrays
     const float4* nb;
     const float4* nc;
     const int2* nd;
+    uint32_t nodes_s;       // shared-memory kernel: shared-window address of node record 0 (already inside the child codes)
+    const char* nodes_g;    // global-memory kernel: DevScene::lnode
 };
+
+// ld.shared by 32-bit shared-window address (a node code of the shared-memory kernel IS such an address)
+#define RT_LDS_F4(v, addr, off) \
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4+" #off "];" : "=f"((v).x), "=f"((v).y), "=f"((v).z), "=f"((v).w) : "r"(addr))
+#define RT_LDS_I2(v, addr, off) asm volatile("ld.shared.v2.s32 {%0,%1}, [%2+" #off "];" : "=r"((v).x), "=r"((v).y) : "r"(addr))
 
 // ---------------------------------------------------------------------------------------------
 // Leaf tests.  `best` is updated iff the candidate wins the reference's min_by: smaller
@@ -435,8 +442,23 @@ __device__ RT_NORM_FN uint32_t quantise(float sum, float spp_f) {
 // 10 FMNMX: the first form saturated the ALU pipe at 75 % with the FMA pipe at 23 %), FMA pre-filter in
 // front of the exact triangle test.  Same while-while structure, same results.
 // ---------------------------------------------------------------------------------------------
+// One node visit's loads.  Shared-memory kernel: the code of an inner node is the shared-window address of its record
+// (no address arithmetic in the loop); global-memory kernel: its byte offset from DevScene::lnode.
+template <bool SMEM>
+__device__ __forceinline__ void load_node(const SceneView& sv, int cur, float4& a, float4& b, float4& c, int2& ch) {
+    if (SMEM) {
+        RT_LDS_F4(a, cur, 0);
+        RT_LDS_F4(b, cur, 16);
+        RT_LDS_F4(c, cur, 32);
+        RT_LDS_I2(ch, cur, 48);
+    } else {
+        const float4* nrec = reinterpret_cast<const float4*>(sv.nodes_g + cur);
+        a = __ldg(nrec); b = __ldg(nrec + 1); c = __ldg(nrec + 2);
+        ch = __ldg(reinterpret_cast<const int2*>(nrec + 3));
+    }
+}
 constexpr int TR_DONE = (int)0x80000000;  // traversal finished (never a leaf code: first_pid < 2^26)
-template <bool COUNT, bool WITH_BIG = true>
+template <bool COUNT, bool WITH_BIG, bool SMEM>
 __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
     best.pid = -1;
     best.dist = 0.0f;
@@ -462,7 +484,7 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
     int stack[MAX_STACK + 1 + MAX_BIG];
     stack[0] = TR_DONE;  // popping the sentinel ends the traversal, so a pop needs no emptiness test
     int* top = stack + 1;  // next free entry
-    if (sc.ltree) *top++ = sc.lroot;
+    if (sc.ltree) *top++ = (SMEM && sc.lroot >= 0) ? sc.lroot + (int)sv.nodes_s : sc.lroot;
 #pragma unroll 1
     for (int i = (int)sc.nbig - 1; WITH_BIG && i >= 0; i--) *top++ = __ldg(&sc.big_code[i]);
 #ifdef RT_AB_POSTPONE
@@ -474,9 +496,9 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
     for (;;) {
         for (;;) {
             if (cur >= 0) {
-                const float4* nrec = sv.na + 3 * cur;
-                const float4 a = nrec[0], b = nrec[1], c = nrec[2];
-                const int2 ch = sv.nd[cur];
+                float4 a, b, c;
+                int2 ch;
+                load_node<SMEM>(sv, cur, a, b, c, ch);
                 const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
                 const float rcx = fmaf(b.z, ix, qx), rcy = fmaf(b.w, iy, qy), rcz = fmaf(c.x, iz, qz);
                 const float tl = fmaxf(fmaxf(fmaf(-a.w, ax, lcx), fmaf(-b.x, ay, lcy)), fmaxf(fmaf(-b.y, az, lcz), 0.0f));
@@ -547,9 +569,9 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
     int cur = *--top;
     for (;;) {
         while (cur >= 0) {
-            const float4* nrec = sv.na + 3 * cur;
-            const float4 a = nrec[0], b = nrec[1], c = nrec[2];
-            const int2 ch = sv.nd[cur];
+            float4 a, b, c;
+            int2 ch;
+            load_node<SMEM>(sv, cur, a, b, c, ch);
             // left box: c = (a.x,a.y,a.z) h = (a.w,b.x,b.y); right: c = (b.z,b.w,c.x) h = (c.y,c.z,c.w)
             const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
             const float rcx = fmaf(b.z, ix, qx), rcy = fmaf(b.w, iy, qy), rcz = fmaf(c.x, iz, qz);
@@ -619,9 +641,9 @@ __device__ __forceinline__ void trace_brute(const DevScene& sc, const SceneView&
     trace_brute_impl<COUNT>(sc, sv, o, d, best, ctr);
     hit_finish(best);
 }
-template <bool COUNT, bool WITH_BIG = true>
+template <bool COUNT, bool WITH_BIG, bool SMEM>
 __device__ __forceinline__ void trace_bvh_ch(const DevScene& sc, const SceneView& sv, V3 o, V3 d, Hit& best, Ctr& ctr) {
-    trace_bvh_ch_impl<COUNT, WITH_BIG>(sc, sv, o, d, best, ctr);
+    trace_bvh_ch_impl<COUNT, WITH_BIG, SMEM>(sc, sv, o, d, best, ctr);
     hit_finish(best);
 }
 
