@@ -413,17 +413,22 @@ int render_and_collect(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, co
     if (rc) return rc;
     const bool streamed = li.counts_done && a.ctl && (a.plan.slabs > 1 || a.tile_ranks > 1);
     SlabJob job;
-    if (streamed) {
+    const bool late = ctx->serial_launches;  // launches block: queue the waits once nothing of ours is outstanding
+    if (streamed && !late) {
         rc = enqueue_slab_copies(ctx, frame_dev, a.ctl, a.plan, seq, out_rgb, tunables().tile_order_reverse != 0, &job);
         if (rc) return rc;
     }
-    if (streamed && job.out && job.pinned != job.out) {  // pageable destination: host copies while the kernel runs
+    if (streamed && !late && job.out && job.pinned != job.out) {  // pageable destination: host copies while the kernel runs
         rc = host_copy_slabs(ctx, job, 0, true, &job.host_done);
         if (rc) return rc;
     }
     uint32_t redone = 0;
     rc = finish_redo(ctx, scene, r, a, &redone);  // own kernel done; pixels it still held back are final (and counted) now
     if (rc) return rc;
+    if (streamed && late) {
+        rc = enqueue_slab_copies(ctx, frame_dev, a.ctl, a.plan, seq, out_rgb, tunables().tile_order_reverse != 0, &job);
+        if (rc) return rc;
+    }
     if (streamed) {
         rc = finish_slab_copies(ctx, job);
         if (rc) return rc;
@@ -461,6 +466,21 @@ int render_rows_to_host(rt_ctx* ctx, const rt_scene* scene, const Resolved& r, u
 }  // namespace
 
 extern "C" {
+
+// Nsight Compute (and CUDA_LAUNCH_BLOCKING=1) make every kernel launch synchronous.  The frame owner normally queues
+// its slab waits, then runs the second pass that releases the pixels its first pass held back (finish_redo); with
+// blocking launches the host would sit in the launch of a wait (or of the kernel behind the value waits) that only its
+// own next step can satisfy — measured: bench.py under ncu stopped at the first streamed frame.  So when launches
+// block, the waits are queued after the second pass.
+static bool launches_block() {
+    extern char** environ;
+    for (char** e = environ; e && *e; e++)
+        if (!strncmp(*e, "NV_NSIGHT_INJECTION", 19) || !strncmp(*e, "NV_COMPUTE_PROFILER", 19) ||
+            !strncmp(*e, "CUDA_INJECTION64_PATH=", 22))
+            return true;
+    const char* b = std::getenv("CUDA_LAUNCH_BLOCKING");
+    return (b && atoi(b) != 0) || std::getenv("RT_B200_SERIAL_LAUNCHES");
+}
 
 int rt_abi_version(void) { return RT_B200_ABI_VERSION; }
 
@@ -522,6 +542,7 @@ int rt_init(int device, rt_ctx** out) {
     ctx->h_flag[0] = 0;
     // load the module and resolve every kernel now: the first division of a job must not pay the lazy load
     CKI(preload_kernels());
+    ctx->serial_launches = launches_block();
     {   // stream memory operations, if this driver and device have them (64-bit waits)
         int can64 = 0;
         void* fn = nullptr;

@@ -137,12 +137,13 @@ __global__ void refit(const unsigned long long* __restrict__ keys, const float* 
         float lc[3], lh[3], rc[3], rh[3];
         centre_half_dev(bl, lc, lh);
         centre_half_dev(br, rc, rh);
-        lnode[4 * (size_t)node + 0] = make_float4(lc[0], lc[1], lc[2], lh[0]);
-        lnode[4 * (size_t)node + 1] = make_float4(lh[1], lh[2], rc[0], rc[1]);
-        lnode[4 * (size_t)node + 2] = make_float4(rc[2], rh[0], rh[1], rh[2]);
+        lnode[NODE_F4 * (size_t)node + 0] = make_float4(lc[0], lc[1], lc[2], lh[0]);
+        lnode[NODE_F4 * (size_t)node + 1] = make_float4(lh[1], lh[2], rc[0], rc[1]);
+        lnode[NODE_F4 * (size_t)node + 2] = make_float4(rc[2], rh[0], rh[1], rh[2]);
         // inner children by the byte offset of their record (rt_device.cuh)
-        reinterpret_cast<int4*>(lnode)[4 * (size_t)node + 3] =
+        reinterpret_cast<int4*>(lnode)[NODE_F4 * (size_t)node + 3] =
             make_int4(cl >= 0 ? cl * NODE_BYTES : cl, cr >= 0 ? cr * NODE_BYTES : cr, 0, 0);
+        for (int k = 4; k < NODE_F4; k++) lnode[NODE_F4 * (size_t)node + k] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
         if (lnode_abc) {  // experiment builds keep the index-coded form as well
             lnode_abc[3 * (size_t)node + 0] = make_float4(lc[0], lc[1], lc[2], lh[0]);
             lnode_abc[3 * (size_t)node + 1] = make_float4(lh[1], lh[2], rc[0], rc[1]);

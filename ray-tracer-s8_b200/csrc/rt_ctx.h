@@ -45,6 +45,7 @@ struct rt_ctx {
     // for a counter in device memory without occupying an SM — the render kernel leaves no room for a waiting kernel
     // (1024 threads x 64 registers = the whole register file of every SM)
     int (*stream_wait_value64)(void* stream, unsigned long long addr, unsigned long long value, unsigned int flags) = nullptr;
+    bool serial_launches = false;         // kernel launches block the host (profiler, CUDA_LAUNCH_BLOCKING): see rt_init
     uint8_t* h_frame = nullptr;           // pinned staging for frames streamed to a pageable destination
     size_t h_frame_bytes = 0;
     std::vector<cudaEvent_t> slab_events; // one per slab, for the pageable path's per-slab host copies

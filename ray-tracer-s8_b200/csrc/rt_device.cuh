@@ -27,18 +27,22 @@ constexpr float T_MAX = 1000.0f; // shapes/mod.rs:13
 // both stored in the DFS leaf order of the reference BVH.  BVH child code: >= 0 inner node index,
 // < 0 leaf with pid = ~code.
 // ---------------------------------------------------------------------------------------------
+// 64 bytes: the same field of different nodes then falls on two of the eight 16-byte bank groups of shared memory (2.3 G
+// bank conflicts on C3, shared wavefronts at 56 % of peak) — an 80-byte record spreads it over all eight and measures
+// the same 36.33 ms (profiles/r2_notes.md), so the smaller record, which keeps larger scenes in shared memory, stays
 constexpr int NODE_BYTES = 64;
+constexpr int NODE_WORDS = NODE_BYTES / 4, NODE_F4 = NODE_BYTES / 16;
 struct DevScene {
     // The first three arrays are adjacent in the scene blob, in this order, each a multiple of 16 bytes:
     //   sph | tri | lnode                      (the shared-memory image of the BVH kernel: ONE bulk copy per CTA)
     const float4* sph;     // [ns]    cx, cy, cz, r*r
     const float4* tri;     // [nt*4]  a | b-a | c-a | normalize_or_zero((a-b)x(a-c))
-    // the traversal tree: one 64-byte record per inner node — two child boxes in centre/half-extent form, padded for
+    // the traversal tree: one NODE_BYTES record per inner node — two child boxes in centre/half-extent form, padded for
     // FILTER rounding (a | b | c: l.c.xyz, l.h.x | l.h.yz, r.c.xy | r.c.z, r.h.xyz), then the two child codes as the
-    // x, y of a fourth int4: >= 0 inner node, as the BYTE OFFSET of its record from lnode (a visit adds a base and
+    // x, y of a fourth int4, then padding: >= 0 inner node, as the BYTE OFFSET of its record from lnode (a visit adds a base and
     // loads; the shared-memory kernel adds the base once, in its image, so its visits load from the code itself),
     // < 0 leaf ~(pid << 5)
-    const float4* lnode;    // [lni*4]
+    const float4* lnode;    // [lni*NODE_F4]
 #ifdef RT_B200_EXPERIMENTS
     const float4* lnode_a;  // [lni*3] the same records as 48 bytes + codes with plain node indices, for the
     const int2* lnode_d;    // [lni]   experiment kernels

@@ -585,7 +585,9 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     }
     for (size_t i = 0; i < (size_t)MAX_BIG; i++)
         ((int32_t*)(h + o_big))[i] = i < big_world.size() ? ~(int32_t)(pid_of_world[big_world[i]] << 5) : 0;
-    *(int32_t*)(h + o_flag) = ref_sync ? 1 : 0;
+    // the flag lives in the late region: inside the staging copy only when the whole blob is uploaded by this call (the
+    // asynchronous path zeroes it on the device above and the builder thread raises it)
+    if (ref_sync) *(int32_t*)(h + o_flag) = 1;
     lap("primitive arrays");
 
     // traversal-tree records from the host tree: DFS pre-order numbering, left subtree first
@@ -609,7 +611,7 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             todo.pop_back();
             const uint32_t me = next++;
             if (it.side < 0) lroot = (int32_t)me * NODE_BYTES;
-            else lc[16 * (size_t)it.parent + 12 + it.side] = (int32_t)me * NODE_BYTES;
+            else lc[NODE_WORDS * (size_t)it.parent + 12 + it.side] = (int32_t)me * NODE_BYTES;
 #ifdef RT_B200_EXPERIMENTS
             if (it.side >= 0) ld[2 * (size_t)it.parent + it.side] = (int32_t)me;
 #endif
@@ -617,18 +619,18 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             float lcn[3], lhh[3], rcn[3], rhh[3];
             centre_half_of(hn.box_l, lcn, lhh);
             centre_half_of(hn.box_r, rcn, rhh);
-            float* pa = ln + 16 * (size_t)me;
+            float* pa = ln + NODE_WORDS * (size_t)me;
             pa[0] = lcn[0]; pa[1] = lcn[1]; pa[2] = lcn[2]; pa[3] = lhh[0];
             pa[4] = lhh[1]; pa[5] = lhh[2]; pa[6] = rcn[0]; pa[7] = rcn[1];
             pa[8] = rcn[2]; pa[9] = rhh[0]; pa[10] = rhh[1]; pa[11] = rhh[2];
-            lc[16 * (size_t)me + 14] = 0; lc[16 * (size_t)me + 15] = 0;
+            for (int k = 14; k < NODE_WORDS; k++) lc[NODE_WORDS * (size_t)me + k] = 0;
 #ifdef RT_B200_EXPERIMENTS
             memcpy(la + 12 * (size_t)me, pa, 48);
 #endif
             const int32_t kids[2] = {hn.left, hn.right};
             for (int side = 1; side >= 0; side--) {  // push right first so the left subtree is numbered first
                 if (kids[side] < 0) {
-                    lc[16 * (size_t)me + 12 + side] = leaf_code(kids[side]);
+                    lc[NODE_WORDS * (size_t)me + 12 + side] = leaf_code(kids[side]);
 #ifdef RT_B200_EXPERIMENTS
                     ld[2 * (size_t)me + side] = leaf_code(kids[side]);
 #endif
