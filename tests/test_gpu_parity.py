@@ -378,6 +378,33 @@ def test_render_before_tables_land(rt, O):
     assert int(got[0].split(":")[1]) < 65536 and int(got[1].split(":")[1]) == 0xffffffff
 
 
+def test_blocking_launches_do_not_deadlock(rt):
+    """With CUDA_LAUNCH_BLOCKING=1 (or under Nsight Compute) every launch blocks the host.  A streamed frame whose first
+    pass held pixels back (tables delayed by RT_B200_AUX_DELAY_MS) used to stop there: the owner sat in a wait for counts
+    only its own second pass releases.  The frame must complete, with the same bytes as without blocking launches."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, hashlib, numpy as np; sys.path.insert(0, 'ray-tracer-s8_b200'); sys.path.insert(0, 'tests');"
+        "import rt_b200 as rt; from test_gpu_parity import _tie_mesh;"
+        "ctx = rt.Context(0); tr = _tie_mesh(rt); sc = ctx.scene(None, tr);"
+        # >= 4 MiB and >= 8 spp: the frame streams to the host slab by slab while it renders
+        "img, st = ctx.render_frame(sc, rt.make_params(1408, 1024, spp=8, max_bounces=2, seed=3), want_stats=True);"
+        "print(hashlib.sha256(img.tobytes()).hexdigest(), st['redo_pixels'])"
+    )
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    got = {}
+    for blocking in ("0", "1"):
+        env = dict(os.environ, RT_B200_AUX_DELAY_MS="200", CUDA_LAUNCH_BLOCKING=blocking)
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, (blocking, out.stderr[-800:])
+        got[blocking] = out.stdout.strip().splitlines()[-1].split()
+    assert got["0"][0] == got["1"][0], got
+    assert int(got["0"][1]) > 0 and int(got["1"][1]) > 0, got
+
+
 def test_pinhole_and_zero_bounce_flags(ctx, rt, O):
     """rt_params.flags: aperture 0 = pinhole and max_bounces 0 = camera rays only, instead of the reference's literals."""
     sp, tr = rt.scenes.synthetic_spheres(40, 9), rt.scenes.ground_plane()

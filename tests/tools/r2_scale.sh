@@ -1,5 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
+timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -2
 for n in 8 4 2 1; do
   timeout 600 python bench.py --gpus $n --steps 20 --warmup 5 --no-extra --no-cpu-baseline > gpurun_out/r2_scale_c3_${n}gpu.json 2> gpurun_out/r2_scale_c3_${n}gpu.err; echo "N=$n exit $?"
   python - <<PY
