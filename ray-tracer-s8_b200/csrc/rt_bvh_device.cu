@@ -137,9 +137,11 @@ __global__ void refit(const unsigned long long* __restrict__ keys, const float* 
         float lc[3], lh[3], rc[3], rh[3];
         centre_half_dev(bl, lc, lh);
         centre_half_dev(br, rc, rh);
-        lnode[NODE_F4 * (size_t)node + 0] = make_float4(lc[0], lc[1], lc[2], lh[0]);
-        lnode[NODE_F4 * (size_t)node + 1] = make_float4(lh[1], lh[2], rc[0], rc[1]);
-        lnode[NODE_F4 * (size_t)node + 2] = make_float4(rc[2], rh[0], rh[1], rh[2]);
+        float w[12];
+        node_box_words(lc, lh, rc, rh, w);
+        lnode[NODE_F4 * (size_t)node + 0] = make_float4(w[0], w[1], w[2], w[3]);
+        lnode[NODE_F4 * (size_t)node + 1] = make_float4(w[4], w[5], w[6], w[7]);
+        lnode[NODE_F4 * (size_t)node + 2] = make_float4(w[8], w[9], w[10], w[11]);
         // inner children by the byte offset of their record (rt_device.cuh)
         reinterpret_cast<int4*>(lnode)[NODE_F4 * (size_t)node + 3] =
             make_int4(cl >= 0 ? cl * NODE_BYTES : cl, cr >= 0 ? cr * NODE_BYTES : cr, 0, 0);

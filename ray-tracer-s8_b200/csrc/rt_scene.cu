@@ -620,12 +620,15 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
             centre_half_of(hn.box_l, lcn, lhh);
             centre_half_of(hn.box_r, rcn, rhh);
             float* pa = ln + NODE_WORDS * (size_t)me;
-            pa[0] = lcn[0]; pa[1] = lcn[1]; pa[2] = lcn[2]; pa[3] = lhh[0];
-            pa[4] = lhh[1]; pa[5] = lhh[2]; pa[6] = rcn[0]; pa[7] = rcn[1];
-            pa[8] = rcn[2]; pa[9] = rhh[0]; pa[10] = rhh[1]; pa[11] = rhh[2];
+            node_box_words(lcn, lhh, rcn, rhh, pa);
             for (int k = 14; k < NODE_WORDS; k++) lc[NODE_WORDS * (size_t)me + k] = 0;
 #ifdef RT_B200_EXPERIMENTS
-            memcpy(la + 12 * (size_t)me, pa, 48);
+            {   // the experiment kernels read the first layout
+                float* q = la + 12 * (size_t)me;
+                q[0] = lcn[0]; q[1] = lcn[1]; q[2] = lcn[2]; q[3] = lhh[0];
+                q[4] = lhh[1]; q[5] = lhh[2]; q[6] = rcn[0]; q[7] = rcn[1];
+                q[8] = rcn[2]; q[9] = rhh[0]; q[10] = rhh[1]; q[11] = rhh[2];
+            }
 #endif
             const int32_t kids[2] = {hn.left, hn.right};
             for (int side = 1; side >= 0; side--) {  // push right first so the left subtree is numbered first
@@ -683,7 +686,16 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     }
     lap("tree records");
 
-    cudaError_t e = cudaMemcpyAsync(sc->d_blob, h, stage_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e;
+    const size_t ln_end = align_up(o_ln + (size_t)lni * NODE_BYTES, 256);
+    if (device_tree && ln_end < stage_bytes) {
+        // the node records are written on the device: nothing of that region is in the staging copy (4 MB at 65,536)
+        e = o_ln ? cudaMemcpyAsync(sc->d_blob, h, o_ln, cudaMemcpyHostToDevice, ctx->stream) : cudaSuccess;
+        if (e == cudaSuccess)
+            e = cudaMemcpyAsync(sc->d_blob + ln_end, h + ln_end, stage_bytes - ln_end, cudaMemcpyHostToDevice, ctx->stream);
+    } else {
+        e = cudaMemcpyAsync(sc->d_blob, h, stage_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    }
     if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);  // the staging buffer is reused by the next scene
     if (e != cudaSuccess) {
         give_back();

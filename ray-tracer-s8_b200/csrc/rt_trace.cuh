@@ -474,6 +474,9 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
     const float qx = -o.x * ix, qy = -o.y * iy, qz = -o.z * iz;
     // rounding of the o-term: <= 3 * 2^-24 * |o*inv| per axis, in t (the c- and h-terms are padded on the host)
     const float slack = 4.8e-7f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 1e-30f;
+#if RT_NODE_XY
+    const f32x2 i_xy = pk2(ix, iy), q_xy = pk2(qx, qy), a_xy = pk2(ax, ay), na_xy = pk2(-ax, -ay);
+#endif
     float cull = 1001.0f;  // a hit has t < T_MAX and length(p-o) ~ t
     const int ns = (int)sc.ns;
     const HitCtx hc = hit_ctx(sc);
@@ -572,6 +575,19 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
             float4 a, b, c;
             int2 ch;
             load_node<SMEM>(sv, cur, a, b, c, ch);
+#if RT_NODE_XY
+            // a = l.c.xy | l.h.xy, b = r.c.xy | r.h.xy, c = l.c.z l.h.z r.c.z r.h.z: x and y of a box in one packed FMA
+            const f32x2 lc2 = fma2(pk2(a.x, a.y), i_xy, q_xy), rc2 = fma2(pk2(b.x, b.y), i_xy, q_xy);
+            const f32x2 ln2 = fma2(na_xy, pk2(a.z, a.w), lc2), lf2 = fma2(a_xy, pk2(a.z, a.w), lc2);
+            const f32x2 rn2 = fma2(na_xy, pk2(b.z, b.w), rc2), rf2 = fma2(a_xy, pk2(b.z, b.w), rc2);
+            const float lcz = fmaf(c.x, iz, qz), rcz = fmaf(c.z, iz, qz);
+            float lnx, lny, lfx, lfy, rnx, rny, rfx, rfy;
+            upk2(ln2, lnx, lny); upk2(lf2, lfx, lfy); upk2(rn2, rnx, rny); upk2(rf2, rfx, rfy);
+            const float tl = fmaxf(fmaxf(lnx, lny), fmaxf(fmaf(-c.y, az, lcz), 0.0f));
+            const float fl = fminf(fminf(lfx, lfy), fminf(fmaf(c.y, az, lcz), cull));
+            const float tr = fmaxf(fmaxf(rnx, rny), fmaxf(fmaf(-c.w, az, rcz), 0.0f));
+            const float fr = fminf(fminf(rfx, rfy), fminf(fmaf(c.w, az, rcz), cull));
+#else
             // left box: c = (a.x,a.y,a.z) h = (a.w,b.x,b.y); right: c = (b.z,b.w,c.x) h = (c.y,c.z,c.w)
             const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
             const float rcx = fmaf(b.z, ix, qx), rcy = fmaf(b.w, iy, qy), rcz = fmaf(c.x, iz, qz);
@@ -579,6 +595,7 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
             const float fl = fminf(fminf(fmaf(a.w, ax, lcx), fmaf(b.x, ay, lcy)), fminf(fmaf(b.y, az, lcz), cull));
             const float tr = fmaxf(fmaxf(fmaf(-c.y, ax, rcx), fmaf(-c.z, ay, rcy)), fmaxf(fmaf(-c.w, az, rcz), 0.0f));
             const float fr = fminf(fminf(fmaf(c.y, ax, rcx), fmaf(c.z, ay, rcy)), fminf(fmaf(c.w, az, rcz), cull));
+#endif
             const bool hl = tl <= fl + slack;
             const bool hr = tr <= fr + slack;
             if (COUNT) ctr.v[CTR_SLAB] += 2;
