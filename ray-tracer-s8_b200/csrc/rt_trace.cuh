@@ -476,6 +476,8 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
     const float slack = 4.8e-7f * fmaxf(fmaxf(fabsf(qx), fabsf(qy)), fabsf(qz)) + 1e-30f;
 #if RT_NODE_XY
     const f32x2 i_xy = pk2(ix, iy), q_xy = pk2(qx, qy), a_xy = pk2(ax, ay), na_xy = pk2(-ax, -ay);
+    const f32x2 i_zz = pk2(iz, iz), q_zz = pk2(qz, qz), a_zz = pk2(az, az), na_zz = pk2(-az, -az);
+    const f32x2 slack2 = pk2(slack, slack);
 #endif
     float cull = 1001.0f;  // a hit has t < T_MAX and length(p-o) ~ t
     const int ns = (int)sc.ns;
@@ -490,85 +492,6 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
     if (sc.ltree) *top++ = (SMEM && sc.lroot >= 0) ? sc.lroot + (int)sv.nodes_s : sc.lroot;
 #pragma unroll 1
     for (int i = (int)sc.nbig - 1; WITH_BIG && i >= 0; i--) *top++ = __ldg(&sc.big_code[i]);
-#ifdef RT_AB_POSTPONE
-    // A/B build (profiles/r2_notes.md): a lane that reaches a leaf keeps it in a register and goes on descending until
-    // it holds two (or runs out of nodes), so that it does node visits instead of idling while its warp's other lanes
-    // are still between leaves; the price is a cull distance that is one leaf stale.
-    int cur = *--top;
-    int pend = 0;  // leaf codes are negative: 0 = none
-    for (;;) {
-        for (;;) {
-            if (cur >= 0) {
-                float4 a, b, c;
-                int2 ch;
-                load_node<SMEM>(sv, cur, a, b, c, ch);
-                const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
-                const float rcx = fmaf(b.z, ix, qx), rcy = fmaf(b.w, iy, qy), rcz = fmaf(c.x, iz, qz);
-                const float tl = fmaxf(fmaxf(fmaf(-a.w, ax, lcx), fmaf(-b.x, ay, lcy)), fmaxf(fmaf(-b.y, az, lcz), 0.0f));
-                const float fl = fminf(fminf(fmaf(a.w, ax, lcx), fmaf(b.x, ay, lcy)), fminf(fmaf(b.y, az, lcz), cull));
-                const float tr = fmaxf(fmaxf(fmaf(-c.y, ax, rcx), fmaf(-c.z, ay, rcy)), fmaxf(fmaf(-c.w, az, rcz), 0.0f));
-                const float fr = fminf(fminf(fmaf(c.y, ax, rcx), fmaf(c.z, ay, rcy)), fminf(fmaf(c.w, az, rcz), cull));
-                const bool hl = tl <= fl + slack;
-                const bool hr = tr <= fr + slack;
-                if (COUNT) ctr.v[CTR_SLAB] += 2;
-                const bool swap = tr < tl;
-                if (hl && hr) *top++ = swap ? ch.x : ch.y;
-                int nxt = (hr && (!hl || swap)) ? ch.y : ch.x;
-                if (!(hl || hr)) nxt = *--top;
-                cur = nxt;
-            } else if (cur != TR_DONE && pend == 0) {
-                pend = cur;
-                cur = *--top;
-            } else {
-                break;
-            }
-        }
-        if (pend == 0 && cur == TR_DONE) return;
-#pragma unroll 1
-        for (int k = 0; k < 2; k++) {
-            const int leaf = k == 0 ? pend : cur;
-            if (leaf >= 0 || leaf == TR_DONE || leaf == 0) continue;
-            const int pid = (~leaf) >> 5;
-            float t = 0.0f;
-            bool cand = false;
-            if (pid < ns) {
-                const float4 s = sv.sph[pid];
-                const V3 oc = mk(x_sub(o.x, s.x), x_sub(o.y, s.y), x_sub(o.z, s.z));
-                const float bh = fmaf(oc.z, d.z, fmaf(oc.y, d.y, oc.x * d.x));
-                const float oc2 = fmaf(oc.z, oc.z, fmaf(oc.y, oc.y, oc.x * oc.x));
-                const float cf = oc2 - s.w;
-                const float disc = fmaf(bh, bh, -cf);
-                if (COUNT) ctr.v[CTR_SPH_TEST]++;
-                if (!(fmaf(oc2, 2e-5f, disc) < 0.0f) && !(bh > 0.0f && cf > 1e-4f * oc2)) {
-                    if (COUNT) ctr.v[CTR_SPH_EXACT]++;
-                    cand = sphere_root_exact(d, oc, s.w, &t);
-                    if (COUNT && cand) ctr.v[CTR_SPH_HIT]++;
-                }
-            } else {
-                if (COUNT) ctr.v[CTR_TRI_TEST]++;
-                if (triangle_filter(sv.tri, pid - ns, o, d, cull)) {
-                    const V3 a = ld3(sv.tri[4 * (pid - ns) + 0]), ab = ld3(sv.tri[4 * (pid - ns) + 1]), ac = ld3(sv.tri[4 * (pid - ns) + 2]);
-                    int stage;
-                    cand = triangle_root_exact(o, d, a, ab, ac, &t, &stage);
-                    if (COUNT) {
-                        if (stage >= 1) ctr.v[CTR_TRI_S1]++;
-                        if (stage >= 2) ctr.v[CTR_TRI_S2]++;
-                        if (stage >= 3) ctr.v[CTR_TRI_S3]++;
-                        if (cand) ctr.v[CTR_TRI_HIT]++;
-                    }
-                }
-            }
-            if (cand) {
-                consider(hc, o, d, t, pid, best);
-                cull = fmaf(best.dist, 1.00001f, 1e-6f);
-            }
-        }
-        pend = 0;
-        if (cur == TR_DONE) return;
-        cur = *--top;
-    }
-}
-#else
     int cur = *--top;
     for (;;) {
         while (cur >= 0) {
@@ -576,17 +499,24 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
             int2 ch;
             load_node<SMEM>(sv, cur, a, b, c, ch);
 #if RT_NODE_XY
-            // a = l.c.xy | l.h.xy, b = r.c.xy | r.h.xy, c = l.c.z l.h.z r.c.z r.h.z: x and y of a box in one packed FMA
+            // a = l.c.xy | l.h.xy, b = r.c.xy | r.h.xy, c = l.c.z r.c.z | l.h.z r.h.z: the eighteen FMAs of the two slab
+            // tests are nine packed ones (x|y of each box, z of both boxes); results are the scalar FMAs' bit for bit
             const f32x2 lc2 = fma2(pk2(a.x, a.y), i_xy, q_xy), rc2 = fma2(pk2(b.x, b.y), i_xy, q_xy);
             const f32x2 ln2 = fma2(na_xy, pk2(a.z, a.w), lc2), lf2 = fma2(a_xy, pk2(a.z, a.w), lc2);
             const f32x2 rn2 = fma2(na_xy, pk2(b.z, b.w), rc2), rf2 = fma2(a_xy, pk2(b.z, b.w), rc2);
-            const float lcz = fmaf(c.x, iz, qz), rcz = fmaf(c.z, iz, qz);
-            float lnx, lny, lfx, lfy, rnx, rny, rfx, rfy;
+            const f32x2 cz2 = fma2(pk2(c.x, c.y), i_zz, q_zz);
+            const f32x2 nz2 = fma2(na_zz, pk2(c.z, c.w), cz2), fz2 = fma2(a_zz, pk2(c.z, c.w), cz2);
+            float lnx, lny, lfx, lfy, rnx, rny, rfx, rfy, lnz, rnz, lfz, rfz;
             upk2(ln2, lnx, lny); upk2(lf2, lfx, lfy); upk2(rn2, rnx, rny); upk2(rf2, rfx, rfy);
-            const float tl = fmaxf(fmaxf(lnx, lny), fmaxf(fmaf(-c.y, az, lcz), 0.0f));
-            const float fl = fminf(fminf(lfx, lfy), fminf(fmaf(c.y, az, lcz), cull));
-            const float tr = fmaxf(fmaxf(rnx, rny), fmaxf(fmaf(-c.w, az, rcz), 0.0f));
-            const float fr = fminf(fminf(rfx, rfy), fminf(fmaf(c.w, az, rcz), cull));
+            upk2(nz2, lnz, rnz); upk2(fz2, lfz, rfz);
+            const float tl = fmaxf(fmaxf(lnx, lny), fmaxf(lnz, 0.0f));
+            const float fl = fminf(fminf(lfx, lfy), fminf(lfz, cull));
+            const float tr = fmaxf(fmaxf(rnx, rny), fmaxf(rnz, 0.0f));
+            const float fr = fminf(fminf(rfx, rfy), fminf(rfz, cull));
+            float fls, frs;
+            upk2(add2(pk2(fl, fr), slack2), fls, frs);
+            const bool hl = tl <= fls;
+            const bool hr = tr <= frs;
 #else
             // left box: c = (a.x,a.y,a.z) h = (a.w,b.x,b.y); right: c = (b.z,b.w,c.x) h = (c.y,c.z,c.w)
             const float lcx = fmaf(a.x, ix, qx), lcy = fmaf(a.y, iy, qy), lcz = fmaf(a.z, iz, qz);
@@ -595,9 +525,9 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
             const float fl = fminf(fminf(fmaf(a.w, ax, lcx), fmaf(b.x, ay, lcy)), fminf(fmaf(b.y, az, lcz), cull));
             const float tr = fmaxf(fmaxf(fmaf(-c.y, ax, rcx), fmaf(-c.z, ay, rcy)), fmaxf(fmaf(-c.w, az, rcz), 0.0f));
             const float fr = fminf(fminf(fmaf(c.y, ax, rcx), fmaf(c.z, ay, rcy)), fminf(fmaf(c.w, az, rcz), cull));
-#endif
             const bool hl = tl <= fl + slack;
             const bool hr = tr <= fr + slack;
+#endif
             if (COUNT) ctr.v[CTR_SLAB] += 2;
             // branch-light step: push and pop are short predicated blocks, the loop has one exit
             const bool swap = tr < tl;
@@ -650,7 +580,6 @@ __device__ __forceinline__ void trace_bvh_ch_impl(const DevScene& sc, const Scen
         cur = *--top;
     }
 }
-#endif
 
 // The queries as the kernels call them: the nearest hit, with Hit::unsure resolved out of the pid bit it travelled in.
 template <bool COUNT>
