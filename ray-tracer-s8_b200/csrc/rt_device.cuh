@@ -203,6 +203,25 @@ struct V3 {
     float x, y, z;
 };
 __device__ __forceinline__ V3 mk(float x, float y, float z) { return V3{x, y, z}; }
+#ifdef RT_PACK_V3
+// x and y of a vector operation as one packed instruction (each half is the scalar round-to-nearest operation)
+__device__ __forceinline__ V3 x_add(V3 a, V3 b) {
+    float x, y;
+    upk2(add2(pk2(a.x, a.y), pk2(b.x, b.y)), x, y);
+    return mk(x, y, x_add(a.z, b.z));
+}
+__device__ __forceinline__ V3 x_sub(V3 a, V3 b) {  // a - b == a + (-b) exactly
+    float x, y;
+    upk2(add2(pk2(a.x, a.y), pk2(-b.x, -b.y)), x, y);
+    return mk(x, y, x_sub(a.z, b.z));
+}
+__device__ __forceinline__ V3 x_scale(V3 a, float s) { return mk(x_mul(a.x, s), x_mul(a.y, s), x_mul(a.z, s)); }
+__device__ __forceinline__ float x_dot(V3 a, V3 b) {
+    float px, py;
+    upk2(mul2(pk2(a.x, a.y), pk2(b.x, b.y)), px, py);
+    return x_add(x_add(px, py), x_mul(a.z, b.z));
+}
+#else
 __device__ __forceinline__ V3 x_add(V3 a, V3 b) { return mk(x_add(a.x, b.x), x_add(a.y, b.y), x_add(a.z, b.z)); }
 __device__ __forceinline__ V3 x_sub(V3 a, V3 b) { return mk(x_sub(a.x, b.x), x_sub(a.y, b.y), x_sub(a.z, b.z)); }
 __device__ __forceinline__ V3 x_scale(V3 a, float s) { return mk(x_mul(a.x, s), x_mul(a.y, s), x_mul(a.z, s)); }
@@ -210,6 +229,7 @@ __device__ __forceinline__ V3 x_scale(V3 a, float s) { return mk(x_mul(a.x, s), 
 __device__ __forceinline__ float x_dot(V3 a, V3 b) {
     return x_add(x_add(x_mul(a.x, b.x), x_mul(a.y, b.y)), x_mul(a.z, b.z));
 }
+#endif
 __device__ __forceinline__ float x_length(V3 a) { return x_sqrt(x_dot(a, a)); }
 // glam cross: (a.zxy*b - a*b.zxy).zxy
 __device__ __forceinline__ V3 x_cross(V3 a, V3 b) {
