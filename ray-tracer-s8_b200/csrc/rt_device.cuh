@@ -174,8 +174,10 @@ __device__ __forceinline__ float x_mul(float a, float b) { return __fmul_rn(a, b
 __device__ __forceinline__ float x_div(float a, float b) { return __fdiv_rn(a, b); }
 __device__ __forceinline__ float x_sqrt(float a) { return __fsqrt_rn(a); }
 
-// Packed FP32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): one issue slot carries two FP32 operations, so an
-// issue-bound FILTER loop can fill the FMA pipe.  FILTER domain only.
+// Packed FP32 pairs (sm_100a FADD2 / FMUL2 / FFMA2): one issue slot carries two FP32 operations, each half rounded
+// like the scalar instruction.  Used where the operands ARE pairs already (node records, sphere pairs); packing the
+// EXACT domain's vector helpers (x and y of x_add / x_sub / x_dot) was measured and lost 2 % to the moves that build
+// the pairs (profiles/r2_notes.md).
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk2(float lo, float hi) {
     f32x2 r;
@@ -203,25 +205,6 @@ struct V3 {
     float x, y, z;
 };
 __device__ __forceinline__ V3 mk(float x, float y, float z) { return V3{x, y, z}; }
-#ifdef RT_PACK_V3
-// x and y of a vector operation as one packed instruction (each half is the scalar round-to-nearest operation)
-__device__ __forceinline__ V3 x_add(V3 a, V3 b) {
-    float x, y;
-    upk2(add2(pk2(a.x, a.y), pk2(b.x, b.y)), x, y);
-    return mk(x, y, x_add(a.z, b.z));
-}
-__device__ __forceinline__ V3 x_sub(V3 a, V3 b) {  // a - b == a + (-b) exactly
-    float x, y;
-    upk2(add2(pk2(a.x, a.y), pk2(-b.x, -b.y)), x, y);
-    return mk(x, y, x_sub(a.z, b.z));
-}
-__device__ __forceinline__ V3 x_scale(V3 a, float s) { return mk(x_mul(a.x, s), x_mul(a.y, s), x_mul(a.z, s)); }
-__device__ __forceinline__ float x_dot(V3 a, V3 b) {
-    float px, py;
-    upk2(mul2(pk2(a.x, a.y), pk2(b.x, b.y)), px, py);
-    return x_add(x_add(px, py), x_mul(a.z, b.z));
-}
-#else
 __device__ __forceinline__ V3 x_add(V3 a, V3 b) { return mk(x_add(a.x, b.x), x_add(a.y, b.y), x_add(a.z, b.z)); }
 __device__ __forceinline__ V3 x_sub(V3 a, V3 b) { return mk(x_sub(a.x, b.x), x_sub(a.y, b.y), x_sub(a.z, b.z)); }
 __device__ __forceinline__ V3 x_scale(V3 a, float s) { return mk(x_mul(a.x, s), x_mul(a.y, s), x_mul(a.z, s)); }
@@ -229,7 +212,6 @@ __device__ __forceinline__ V3 x_scale(V3 a, float s) { return mk(x_mul(a.x, s), 
 __device__ __forceinline__ float x_dot(V3 a, V3 b) {
     return x_add(x_add(x_mul(a.x, b.x), x_mul(a.y, b.y)), x_mul(a.z, b.z));
 }
-#endif
 __device__ __forceinline__ float x_length(V3 a) { return x_sqrt(x_dot(a, a)); }
 // glam cross: (a.zxy*b - a*b.zxy).zxy
 __device__ __forceinline__ V3 x_cross(V3 a, V3 b) {
