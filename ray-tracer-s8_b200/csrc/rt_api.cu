@@ -183,7 +183,7 @@ static int read_counters(rt_ctx* ctx) {
     CK(ctx, cudaStreamSynchronize(ctx->stream));
     if (ctx->h_flag[0]) {
         ctx->h_flag[0] = 0;
-        return set_err(ctx, RT_ERR_TIMEOUT, "waited 20 s for the frame's owner (rt_frame_wait_consumed)");
+        return set_err(ctx, RT_ERR_TIMEOUT, "waited %d ms for a frame counter (the owner's \"consumed\" word, or a slab of the frame)", tunables().wait_timeout_ms);
     }
     return RT_OK;
 }
@@ -345,7 +345,7 @@ static int host_copy_slabs(rt_ctx* ctx, const SlabJob& job, uint32_t first, bool
         } else {
             const auto t0 = std::chrono::steady_clock::now();
             while (cudaEventQuery(ctx->slab_events[s]) != cudaSuccess) {
-                if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+                if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(tunables().wait_timeout_ms)) {
                     (void)cudaGetLastError();
                     *done_out = i;
                     return RT_OK;  // finish_slab_copies' drain reports the timeout
@@ -369,7 +369,7 @@ static int drain_copy_stream(rt_ctx* ctx, const SlabJob& job) {
         const cudaError_t q = cudaStreamQuery(ctx->copy_stream);
         if (q == cudaSuccess) break;
         if (q != cudaErrorNotReady) return set_err(ctx, RT_ERR_CUDA, "copy stream: %s", cudaGetErrorString(q));
-        if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(20)) {
+        if (std::chrono::steady_clock::now() - t0 > std::chrono::milliseconds(tunables().wait_timeout_ms)) {
             ctx->h_flag[0] = 1;
             if (job.ctl) {
                 unsigned long long* fill = ctx->h_ctr;  // pinned scratch: RT_CTR_SLOTS >= MAX_SLABS entries
@@ -395,7 +395,10 @@ int finish_slab_copies(rt_ctx* ctx, const SlabJob& job) {
     }
     const int rc = drain_copy_stream(ctx, job);
     if (rc) return rc;
-    if (ctx->h_flag[0]) return set_err(ctx, RT_ERR_TIMEOUT, "a slab of the frame did not complete within 20 s");
+    if (ctx->h_flag[0]) {
+        ctx->h_flag[0] = 0;  // reported here: the next call starts clean
+        return set_err(ctx, RT_ERR_TIMEOUT, "a slab of the frame did not complete within %d ms", tunables().wait_timeout_ms);
+    }
     return RT_OK;
 }
 

@@ -29,6 +29,7 @@ struct Tunables {
     bool async_ref = true;       // RT_B200_ASYNC_REF=0: build the reference-topology tree inside rt_scene_create
     int pid_order = 1;           // RT_B200_PID_ORDER=world: primitive ids in world order instead of the traversal tree's DFS order
     int aux_delay_ms = 0;        // RT_B200_AUX_DELAY_MS: the builder thread sleeps first (tests: frames rendered before the tables land)
+    int wait_timeout_ms = 20000; // RT_B200_WAIT_TIMEOUT_MS: how long a frame owner waits for a slab / a rank for the owner
     bool count_done = true;      // RT_B200_COUNT_DONE=0: no completion counters (frames are copied after the kernel)
 #ifdef RT_B200_EXPERIMENTS
     int bvh_variant = 3;         // RT_B200_BVH_KERNEL=lanes|simple|pools|deferred|wave|wq

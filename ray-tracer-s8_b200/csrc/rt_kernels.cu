@@ -541,6 +541,7 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
 // device→host copy of that slab on the copy stream.  Bounded: a rank that died must not hang the frame owner.
 __global__ void wait_slab_kernel(const unsigned long long* done, unsigned long long target, unsigned int* timeout_flag,
                                  unsigned long long max_ns) {
+    if (*reinterpret_cast<volatile unsigned int*>(timeout_flag)) return;  // an earlier wait of this frame gave up already
     unsigned long long t0;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
     for (;;) {
@@ -650,6 +651,7 @@ const Tunables& tunables() {
         v.count_done = env_int("RT_B200_COUNT_DONE", 1) != 0;
         v.pid_order = env_is("RT_B200_PID_ORDER", "world") ? 0 : 1;
         v.aux_delay_ms = std::max(0, env_int("RT_B200_AUX_DELAY_MS", 0));
+        v.wait_timeout_ms = std::max(1, env_int("RT_B200_WAIT_TIMEOUT_MS", 20000));
 #ifdef RT_B200_EXPERIMENTS
         read_experiment_tunables(&v);
 #endif
@@ -788,13 +790,14 @@ cudaError_t launch_render(const DevScene& sc, const DevCamera& cam, const DevPar
 
 cudaError_t launch_wait_slab(const unsigned long long* done, unsigned long long target, unsigned int* timeout_flag,
                              cudaStream_t stream) {
-    wait_slab_kernel<<<1, 1, 0, stream>>>(done, target, timeout_flag, 20ull * 1000000000ull);
+    wait_slab_kernel<<<1, 1, 0, stream>>>(done, target, timeout_flag, (unsigned long long)tunables().wait_timeout_ms * 1000000ull);
     return cudaGetLastError();
 }
 
 cudaError_t launch_wait_all_slabs(const unsigned long long* done, unsigned long long seq, uint32_t slabs, uint32_t tile_rows,
                                   uint32_t rows, uint32_t width, unsigned int* timeout_flag, cudaStream_t stream) {
-    wait_all_slabs_kernel<<<1, MAX_SLABS, 0, stream>>>(done, seq, slabs, tile_rows, rows, width, timeout_flag, 20ull * 1000000000ull);
+    wait_all_slabs_kernel<<<1, MAX_SLABS, 0, stream>>>(done, seq, slabs, tile_rows, rows, width, timeout_flag,
+                                                       (unsigned long long)tunables().wait_timeout_ms * 1000000ull);
     return cudaGetLastError();
 }
 

@@ -405,6 +405,39 @@ def test_blocking_launches_do_not_deadlock(rt):
     assert int(got["0"][1]) > 0 and int(got["1"][1]) > 0, got
 
 
+def test_owner_times_out_when_a_slab_never_completes(rt):
+    """A frame nobody renders into: the owner's collect must give up after the wait limit with RT_ERR_TIMEOUT — by value
+    waits (the host satisfies the counters itself so the copy stream drains) and by wait kernels — and leave the
+    context usable."""
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, time, hashlib, numpy as np; sys.path.insert(0, 'ray-tracer-s8_b200');"
+        "import rt_b200 as rt; from rt_b200 import scenes, _abi;"
+        "ctx = rt.Context(0); p = rt.make_params(256, 192, spp=1, max_bounces=2, seed=1);"
+        "dev, handle = ctx.frame_alloc(256 * 192 * 3); t0 = time.time(); status = 0\n"
+        "try:\n"
+        "    ctx.frame_collect(dev, p, 1, out=np.empty((192, 256, 3), np.uint8))\n"
+        "except rt.RtError as e:\n"
+        "    status = e.status\n"
+        "dt = time.time() - t0\n"
+        "sc = ctx.scene(scenes.synthetic_spheres(40, 3), scenes.ground_plane()).wait_ready()\n"
+        "a = ctx.render_frame(sc, p); b = ctx.render_frame(sc, p)\n"
+        "print(status, round(dt, 2), int((a == b).all()), int(a.max()))"
+    )
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    for extra in ({}, {"RT_B200_NO_STREAM_WAIT": "1"}):
+        env = dict(os.environ, RT_B200_WAIT_TIMEOUT_MS="400", **extra)
+        out = subprocess.run([sys.executable, "-c", code], cwd=root, env=env, capture_output=True, text=True, timeout=120)
+        assert out.returncode == 0, (extra, out.stderr[-800:])
+        status, dt, same, mx = out.stdout.strip().splitlines()[-1].split()
+        assert int(status) == -9, (extra, out.stdout)          # RT_ERR_TIMEOUT
+        assert 0.3 <= float(dt) < 10.0, (extra, dt)
+        assert same == "1" and int(mx) > 0, (extra, out.stdout)
+
+
 def test_pinhole_and_zero_bounce_flags(ctx, rt, O):
     """rt_params.flags: aperture 0 = pinhole and max_bounces 0 = camera rays only, instead of the reference's literals."""
     sp, tr = rt.scenes.synthetic_spheres(40, 9), rt.scenes.ground_plane()
