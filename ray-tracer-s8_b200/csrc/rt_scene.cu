@@ -230,8 +230,8 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
 #endif
     const int tree_mode = tn.tree_mode;
     std::vector<uint32_t> big_world;  // split layout: world positions of the primitives kept out of the tree
-    std::vector<Box> rest;            // boxes and world positions of the primitives the tree covers
-    std::vector<uint32_t> rest_world;
+    std::vector<Box> rest_store;      // boxes and world positions of the primitives the tree covers (split layout only:
+    std::vector<uint32_t> rest_world; //   without big primitives the tree covers `boxes` itself, no copy)
     if (tree_mode == 2 && n > 1) {
         auto area_of = [](const Box& b) {
             const double sx = (double)b.max[0] - b.min[0], sy = (double)b.max[1] - b.min[1], sz = (double)b.max[2] - b.min[2];
@@ -255,20 +255,22 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
         std::sort(big_world.begin(), big_world.end());
     }
     if (big_world.empty()) {
-        rest = boxes;
         rest_world.resize(n);
         for (uint32_t w = 0; w < n; w++) rest_world[w] = w;
     } else {
         size_t bi = 0;
+        rest_store.reserve(n - big_world.size());
+        rest_world.reserve(n - big_world.size());
         for (uint32_t w = 0; w < n; w++) {
             if (bi < big_world.size() && big_world[bi] == w) {
                 bi++;
                 continue;
             }
-            rest.push_back(boxes[w]);
+            rest_store.push_back(boxes[w]);
             rest_world.push_back(w);
         }
     }
+    const std::vector<Box>& rest = big_world.empty() ? boxes : rest_store;
     const bool ltree = !rest.empty();
     constexpr uint32_t kDeviceBuildMin = 8192;
     const bool device_tree = tree_mode != 0 && rest.size() >= 2 &&
