@@ -362,7 +362,8 @@ static int host_copy_slabs(rt_ctx* ctx, const SlabJob& job, uint32_t first, bool
     return RT_OK;
 }
 
-// A stream that waits by value has no time limit of its own: give up after 20 s by satisfying every wait from the side.
+// A stream that waits by value has no time limit of its own: when the wait limit (RT_B200_WAIT_TIMEOUT_MS, 20 s) is
+// over, every wait is satisfied from the side and the caller reports the timeout.
 static int drain_copy_stream(rt_ctx* ctx, const SlabJob& job) {
     const auto t0 = std::chrono::steady_clock::now();
     for (;;) {
