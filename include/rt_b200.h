@@ -140,7 +140,10 @@ const char* rt_last_error(const rt_ctx* ctx);
 /* ---- scene: replaces `req.world` ownership + BVH::build (main.rs:60-61) ------------------------- */
 /* world_index (nullable): position of each primitive in the reference's Vec<Object>, spheres first
  * then triangles, a permutation of 0..n-1.  NULL = spheres in order, then triangles.  The world order
- * decides exact-distance ties the way the reference's BVH leaf order does (shapes/mod.rs:177-182). */
+ * decides exact-distance ties the way the reference's BVH leaf order does (shapes/mod.rs:177-182).
+ * RT_ERR_EMPTY_SCENE for an empty world (the reference's build never terminates on it), RT_ERR_UNSUPPORTED above
+ * 2^25 primitives (tree node offsets are 31 bits of 64-byte records) or when the traversal tree is deeper than the
+ * traversal stack (64). */
 int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, const rt_triangle* triangles,
                     uint32_t n_triangles, const uint32_t* world_index, rt_scene** out);
 void rt_scene_destroy(rt_ctx* ctx, rt_scene* scene);

@@ -195,8 +195,11 @@ int rt_scene_create(rt_ctx* ctx, const rt_sphere* spheres, uint32_t n_spheres, c
     if (n64 == 0)
         return set_err(ctx, RT_ERR_EMPTY_SCENE,
                        "empty world: the reference's BVHNode::build never terminates on zero shapes");
-    if (n64 > 0x3ffffffu)  // leaf codes are ~((first_pid << 5) | (count - 1)) in 32 bits
-        return set_err(ctx, RT_ERR_UNSUPPORTED, "too many primitives (%llu; this build holds primitive ids in 26 bits)", (unsigned long long)n64);
+    // leaf codes are ~(pid << 5) in 32 bits (26-bit ids); inner codes are the byte offset of a 64-byte node record and
+    // must stay positive (n - 1 records: 25 bits of nodes)
+    if (n64 > 0x3ffffffu || (n64 - 1) * (uint64_t)NODE_BYTES > 0x7fffffffull)
+        return set_err(ctx, RT_ERR_UNSUPPORTED, "too many primitives (%llu; this build addresses %llu)", (unsigned long long)n64,
+                       (unsigned long long)(0x7fffffffull / NODE_BYTES + 1));
     if ((n_spheres && !spheres) || (n_triangles && !triangles))
         return set_err(ctx, RT_ERR_INVALID_ARG, "rt_scene_create: NULL primitive array");
     const uint32_t n = (uint32_t)n64;

@@ -581,6 +581,13 @@ def test_error_codes(ctx, rt):
     with pytest.raises(rt.RtError) as e:
         ctx.render_division(sc, rt.make_params(16, 8, divisions=2, division_no=2, spp=1, max_bounces=1))
     assert e.value.status == -1
+    # more primitives than node byte offsets (31 bits / 64-byte records) or primitive ids (26 bits) can address: refused
+    # before anything is read
+    import ctypes as C
+    h = C.c_void_p()
+    for count in (2**25 + 1, 2**26 + 5):
+        rc = ctx._lib.rt_scene_create(ctx._h, None, count, None, 0, None, C.byref(h))
+        assert rc == -6 and b"too many primitives" in ctx._lib.rt_last_error(ctx._h), (count, rc)
     # the context stays usable after errors
     img = ctx.render_frame(sc, rt.make_params(16, 8, spp=1, max_bounces=1))
     assert img.shape == (8, 16, 3)
