@@ -438,6 +438,32 @@ def test_owner_times_out_when_a_slab_never_completes(rt):
         assert same == "1" and int(mx) > 0, (extra, out.stdout)
 
 
+def test_scene_sizes_around_staging_capacity(rt, O):
+    """The pinned staging copy of an asynchronously built scene covers the early part of the blob only; its capacity is
+    a power of two.  Worlds whose early part just fits a capacity while the late tables do not (13-14 k and 27-28 k
+    spheres for 2 and 4 MiB) once had their "tables landed" flag written past the buffer.  Create, render, compare."""
+    import hashlib
+    import os
+    import subprocess
+    import sys
+
+    code = (
+        "import sys, hashlib; sys.path.insert(0, 'ray-tracer-s8_b200'); import rt_b200 as rt; from rt_b200 import scenes;"
+        "ctx = rt.Context(0); out = []\n"
+        "for n in (13000, 14000, 27500):\n"
+        "    sc = ctx.scene(scenes.synthetic_spheres(n, 2), None)\n"
+        "    img = ctx.render_frame(sc, rt.make_params(96, 64, spp=1, max_bounces=3, seed=5))\n"
+        "    sc.wait_ready(); out.append(hashlib.sha256(img.tobytes()).hexdigest()); sc.close()\n"
+        "print(' '.join(out))"
+    )
+    root = os.path.abspath(os.path.join(os.path.dirname(__file__), ".."))
+    out = subprocess.run([sys.executable, "-c", code], cwd=root, env=dict(os.environ), capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, (out.returncode, out.stderr[-800:])
+    got = out.stdout.strip().splitlines()[-1].split()
+    ref, _ = O.render_frame(rt.scenes.synthetic_spheres(14000, 2), None, 96, 64, 1, 3, seed=5)
+    assert got[1] == hashlib.sha256(ref.tobytes()).hexdigest()
+
+
 def test_pinhole_and_zero_bounce_flags(ctx, rt, O):
     """rt_params.flags: aperture 0 = pinhole and max_bounces 0 = camera rays only, instead of the reference's literals."""
     sp, tr = rt.scenes.synthetic_spheres(40, 9), rt.scenes.ground_plane()
