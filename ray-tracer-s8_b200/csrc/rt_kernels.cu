@@ -12,8 +12,9 @@
 //     copy of the scene per SM and the rest of the 228 KB left to L1 for the traversal stacks
 //   * output: finished pixels are staged in a per-warp shared-memory tile; a complete tile leaves as twelve
 //     8-byte row vectors (the frame may be peer memory: these are the NVLink stores of the fused render + gather)
-//   * completion: one system-scope release per tile adds its pixel count to the slab's counter in the frame's
-//     control block, so the frame owner copies finished slabs to the host while the rest still renders
+//   * completion: the lane that completes a tile adds its pixel count to the warp's batching word; one system-scope
+//     release (red.release.sys) per warp and slab adds it to the slab's counter in the frame's control block, which the
+//     frame owner's copy stream waits on by value: finished slabs reach the host while the rest still renders
 //   * tail: the last tickets are handed out pixel by pixel, so no lane idles while a neighbour finishes a tile
 //
 // The nearest-hit query itself (K1 brute force / K2 BVH) lives in rt_trace.cuh.
@@ -537,8 +538,11 @@ __global__ void __launch_bounds__(TPB, MINB) render_kernel_lanes(const DevScene 
     }
 }
 
-// Spins (one thread) until the slab counter of a frame's control block reaches `target`; ordered before the
-// device→host copy of that slab on the copy stream.  Bounded: a rank that died must not hang the frame owner.
+// Spins (one thread) until a counter of a frame's control block reaches `target`.  Used by the ranks that wait for the
+// owner's "consumed" word in front of their next kernel, and — only when the driver has no 64-bit stream waits
+// (rt_init: cuStreamWaitValue64) — by the owner in front of each slab's device→host copy: beside 1024-thread CTAs that
+// own every register of their SM such a kernel becomes resident only when the render kernel ends.  Bounded: a rank
+// that died must not hang anybody.
 __global__ void wait_slab_kernel(const unsigned long long* done, unsigned long long target, unsigned int* timeout_flag,
                                  unsigned long long max_ns) {
     if (*reinterpret_cast<volatile unsigned int*>(timeout_flag)) return;  // an earlier wait of this frame gave up already
